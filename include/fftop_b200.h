@@ -1,0 +1,178 @@
+/*
+ * fftop_b200.h -- C ABI of libfftop_b200.so, the B200 (sm_100a) batched Fourier option-pricing
+ * engine.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * The reference (danielhstahl/FFTOptionPricing) is a header-only C++14 template library with no
+ * ABI of its own.  Each entry point below is the batched, descriptor-driven
+ * equivalent of one family of reference templates; the reference interface it replaces is cited
+ * as file:line relative to the reference tree.  The reference takes an arbitrary C++ callable as
+ * characteristic function (CF); device code cannot, so the CF is a *model descriptor*
+ * (fop_model_t) covering exactly the CFs the reference's tests and calibration driver use
+ * (test.cpp:54,570,731,887-905,989,1050,1090,1119; generateCharts.cpp:190-380).
+ *
+ * Conventions
+ *  - Every array argument may be a HOST or a DEVICE pointer (detected with
+ *    cudaPointerGetAttributes).  Host inputs are staged through pinned workspace owned by the
+ *    handle; host outputs are copied back and the call returns after the stream is idle.  When all
+ *    outputs are device pointers the call only enqueues work on the handle's stream
+ *    (fop_get_stream) and returns; use fop_synchronize or your own events.
+ *  - All arithmetic is IEEE fp64.  No fast-math, exact sincospi twiddles.
+ *  - Return value: FOP_OK or an error class; fop_last_error(h) gives the message.
+ *    Like the reference (which validates nothing) NaNs in parameters propagate to the
+ *    outputs; only structural errors (null pointers, non power-of-two N, sizes out of the
+ *    supported range, unknown enum) are reported.
+ *  - A handle is bound to one device and is not thread-safe; use one handle per host thread/GPU.
+ *  - There is NO CPU fallback: without a CUDA device fop_create fails with FOP_CUDA_ERROR.
+ */
+#ifndef FFTOP_B200_H
+#define FFTOP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOP_ABI_VERSION 1
+
+typedef struct fop_handle_s* fop_handle_t;
+
+enum fop_status {
+  FOP_OK = 0,
+  FOP_INVALID_ARG = 1,
+  FOP_CUDA_ERROR = 2,
+  FOP_OOM = 3,
+  FOP_UNSUPPORTED = 4
+};
+
+/* ---- characteristic-function model descriptor ------------------------------------------------
+ * Levy base (per unit time, risk-neutral log CF psi(u), u complex):
+ *   FOP_GAUSS  params [sigma]                    gaussLogCF(u, r-sigma^2/2, sigma)      test.cpp:570
+ *   FOP_MERTON params [sigma, lambda, muJ, sigJ] mertonLogRNCF(u,lambda,muJ,sigJ,r,sigma) test.cpp:1119
+ *   FOP_CGMY   params [sigma, C, G, M, Y]        cgmyLogRNCF(u,C,G,M,Y,r,sigma)         test.cpp:731
+ * Time change (4 more params appended: [speed, adaV, rho, v0Hat]):
+ *   FOP_TC_NONE           phi(u) = exp(psi_r(u) T)
+ *   FOP_TC_CIR            phi(u) = exp(r T u + cirLogMGF(-psi_0(u), speed, speed-adaV rho u sigma,
+ *                                                        adaV, T, v0Hat))   test.cpp:887-894,1049-1058
+ *                         (GAUSS + CIR is the reference's "Heston", generateCharts.cpp:231-250)
+ *   FOP_TC_CIR_DIFFUSION  only the Brownian part is time changed, jumps run in calendar time
+ *                                                                           test.cpp:896-905
+ * Parameter order follows generateCharts.cpp:215,260,306,346.
+ */
+enum fop_base_model { FOP_GAUSS = 0, FOP_MERTON = 1, FOP_CGMY = 2 };
+enum fop_time_change { FOP_TC_NONE = 0, FOP_TC_CIR = 1, FOP_TC_CIR_DIFFUSION = 2 };
+
+typedef struct fop_model_s {
+  int base;        /* enum fop_base_model  */
+  int time_change; /* enum fop_time_change */
+} fop_model_t;
+
+/* number of doubles per parameter set for a model (0 if the descriptor is invalid) */
+int fop_model_num_params(fop_model_t model);
+
+/* COS output kinds: OptionPricing.h:362 (CallPrice) :398 (PutPrice) :423 :448 (Delta)
+ * :525 :550 (Gamma) :474 :499 (Theta) */
+enum fop_cos_kind {
+  FOP_CALL_PRICE = 0,
+  FOP_PUT_PRICE = 1,
+  FOP_CALL_DELTA = 2,
+  FOP_PUT_DELTA = 3,
+  FOP_CALL_GAMMA = 4,
+  FOP_PUT_GAMMA = 5,
+  FOP_CALL_THETA = 6,
+  FOP_PUT_THETA = 7
+};
+
+/* FSTS output kinds: OptionPricing.h:186 (Price) :210 (Delta) :235 (Theta) :259 (Gamma) */
+enum fop_fsts_kind { FOP_FSTS_PRICE = 0, FOP_FSTS_DELTA = 1, FOP_FSTS_GAMMA = 2, FOP_FSTS_THETA = 3 };
+/* payoff of the asset K*exp(x): call max(S-K,0), put max(K-S,0)   test.cpp:56-61,202-204 */
+enum fop_payoff { FOP_PAYOFF_CALL = 0, FOP_PAYOFF_PUT = 1 };
+
+/* ---- handle ---------------------------------------------------------------------------------- */
+int fop_abi_version(void);
+int fop_create(fop_handle_t* handle, int device_ordinal);
+int fop_destroy(fop_handle_t handle);
+const char* fop_last_error(fop_handle_t handle); /* valid until the next call on the handle */
+const char* fop_status_string(int status);
+void* fop_get_stream(fop_handle_t handle);       /* the handle's cudaStream_t */
+int fop_synchronize(fop_handle_t handle);
+/* number of this library's kernel launches since fop_create (for bench.py's gpu_launches) */
+long long fop_launch_count(fop_handle_t handle);
+
+/* ---- grid helpers (host, trivial) ------------------------------------------------------------ */
+/* getCarrMadanStrikes            OptionPricing.h:131-138: K_i = S0 exp(-pi/ada + (2 pi/ada/N) i) */
+int fop_carr_madan_strikes(int N, double ada, double S0, double* K_out);
+/* getFangOostStrike              OptionPricing.h:98-105:  K_i = S0 exp(-(xMin + dx i))           */
+int fop_fang_oost_strikes(double xMin, double xMax, double S0, int numX, double* K_out);
+/* getStrikeUnderlying            OptionPricing.h:84-90:   S_i = K exp(xMin + dx i)               */
+int fop_strike_underlying(double xMin, double xMax, double K, int numX, double* S_out);
+
+/* ---- Carr-Madan ------------------------------------------------------------------------------
+ * Replaces optionprice::CarrMadanCall / CarrMadanPut (OptionPricing.h:620-656, :670-704; pass
+ * alpha = 1.5 for the 6-argument overloads) and CarrMadanGeneric (:582-607), batched over P
+ * parameter sets.  N must be a power of two, 2 <= N <= 2^20.
+ *   params [P][np]   out [P][N]   (index i <-> strike fop_carr_madan_strikes()[i])
+ */
+int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int P, int N,
+                   double ada, double alpha, double S0, double r, double T, int is_put,
+                   double* out);
+
+/* ---- Fang-Oosterlee COS ----------------------------------------------------------------------
+ * Replaces optionprice::FangOost{Call,Put}{Price,Delta,Gamma,Theta} (OptionPricing.h:358-559) and
+ * FangOostGeneric (:325-346) including the absent fangoost::computeExpectationVectorLevy,
+ * batched over P parameter sets and M maturities.
+ *   K_desc [J] strikes in DESCENDING order, first and last are the synthetic far strikes
+ *              (OptionPricing.h:303-312,351)
+ *   T [M]      maturities;   numU <= 1024;   out [P][M][J]
+ */
+int fop_cos(fop_handle_t h, fop_model_t model, const double* params, int P,
+            const double* K_desc, int J, double S0, double r, const double* T, int M, int numU,
+            int kind, double* out);
+
+/* ---- FSTS ------------------------------------------------------------------------------------
+ * Replaces optionprice::FSTS{Price,Delta,Gamma,Theta} (OptionPricing.h:185-281) and FSTSGeneric
+ * (:155-184): steps = 1, american = 0 is the reference's single FFT -> multiply -> IFFT.
+ * steps > 1 applies the one-step operator with dt = T/steps repeatedly; american != 0 takes
+ * max(value, payoff) after every step (README.md:19 -- not implemented by the reference; defined
+ * in SURVEY.md A.4).  steps > 1 needs a Levy model (FOP_TC_NONE) and kind FOP_FSTS_PRICE.
+ * N power of two, 4 <= N <= 8192.   out [P][N]  (node j <-> asset fop_strike_underlying(-xmax,
+ * xmax, strike, N)[j])
+ */
+int fop_fsts(fop_handle_t h, fop_model_t model, const double* params, int P, int N, double xmax,
+             double strike, double r, double T, int steps, int american, int payoff, int kind,
+             double* out);
+
+/* ---- calibration objectives ------------------------------------------------------------------
+ * fop_objfn_cf replaces the closure returned by optioncal::getObjFn_arr
+ * (OptionCalibration.h:185-201) evaluated for P parameter vectors at once:
+ *   loss_p = (1/m) sum_l ( isnan(c) ? 5000 : |phiHat_l - c|^2 ),  c = logCF_p(1 + i u_l)
+ * where logCF is the model's log characteristic function at maturity T with rate r
+ * (generateCharts.cpp:231-250 uses r = 0).   u [m], phiHat [m][2] (re, im), loss [P].
+ */
+int fop_objfn_cf(fop_handle_t h, fop_model_t model, const double* params, int P,
+                 const double* u, const double* phiHat, int m, double r, double T,
+                 double* loss);
+
+/* Price-space objective (BASELINE.json config 5; defined in SURVEY.md 8c-ii on top of
+ * FangOostCallPrice, OptionPricing.h:362-382):
+ *   loss_p = (1/(M J)) sum_{m,j} w_mj (FangOostCallPrice_pmj - mkt_mj)^2
+ * mkt [M][J], w [M][J] or NULL (all ones), loss [P]; prices_out [P][M][J] or NULL.
+ */
+int fop_cos_loss(fop_handle_t h, fop_model_t model, const double* params, int P,
+                 const double* K_desc, int J, double S0, double r, const double* T, int M,
+                 int numU, const double* mkt, const double* w, double* loss,
+                 double* prices_out);
+
+/* ---- batched FFT (the replacement for fft.hpp:49-61; exposed for parity tests) ---------------
+ * In-place unnormalised transforms of `batch` contiguous length-N complex128 sequences
+ * (interleaved re,im -- the layout of the reference's CArray, fft.h:12-13).
+ * inverse = 0: X_m = sum_j x_j e^{-2 pi i jm/N} (fft.hpp:56);  inverse = 1: e^{+...} (fft.hpp:49).
+ * N power of two, 2 <= N <= 2^20.
+ */
+int fop_fft(fop_handle_t h, double* data, int batch, int N, int inverse);
+
+/* measured fp64 FMA throughput of the device in TFLOP/s (roofline denominator, bench.py) */
+int fop_measure_fp64_peak(fop_handle_t h, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFTOP_B200_H */

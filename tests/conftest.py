@@ -1,0 +1,66 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# Parity bar of BASELINE.json north_star: |gpu - ref| <= 1e-8 + 1e-10 |ref| (fp64).
+ATOL = 1e-8
+RTOL = 1e-10
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+
+
+def assert_parity(got, ref, atol=ATOL, rtol=RTOL, what=""):
+    got = np.asarray(got, dtype=np.float64).reshape(-1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(-1)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    both_nan = np.isnan(got) & np.isnan(ref)
+    err = np.abs(got - ref)
+    tol = atol + rtol * np.abs(ref)
+    bad = ~both_nan & ~(err <= tol)
+    if bad.any():
+        i = int(np.argmax(np.where(bad, err / tol, 0)))
+        raise AssertionError(
+            f"{what}: {int(bad.sum())}/{got.size} outside {atol:g}+{rtol:g}|ref|; worst at {i}: "
+            f"got {got[i]!r} ref {ref[i]!r} err {err[i]:.3e} tol {tol[i]:.3e}")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(ROOT, "tests", "golden", "golden_v1.json")) as f:
+        g = json.load(f)
+    return {c["name"]: c for c in g["cases"]}
+
+
+def golden_expect(entry, out):
+    """Select from `out` the entries the golden file kept; returns (got, expected)."""
+    out = np.asarray(out, dtype=np.float64).reshape(-1)
+    assert out.size == entry["n"], f"{entry['name']}: size {out.size} vs golden {entry['n']}"
+    exp = np.asarray(entry["values"], dtype=np.float64)
+    got = out if entry["idx"] is None else out[np.asarray(entry["idx"])]
+    return got, exp
+
+
+@pytest.fixture(scope="session")
+def oracles():
+    """Builds the port (always) and returns {'port': Oracle, 'reference': Oracle or None}."""
+    from oracle import build as obuild
+    from oracle import oracle as O
+    obuild.build()
+    out = {"port": O.load("port"), "reference": None}
+    if O.available("reference"):
+        out["reference"] = O.load("reference")
+    return out
+
+
+@pytest.fixture(scope="session")
+def best_oracle(oracles):
+    return oracles["reference"] or oracles["port"]
