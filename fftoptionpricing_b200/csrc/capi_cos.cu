@@ -1,0 +1,193 @@
+// C ABI: fop_cos, fop_cos_loss  (Fang-Oosterlee COS; include/fftop_b200.h)
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "cos_kernels.cuh"
+#include "handle.cuh"
+
+namespace {
+using namespace fop;
+
+struct CosVariant {
+  int TR, TJ, WR;
+  void (*kernel)(const CosArgs);
+};
+#define COS_V(TR, TJ, WR) \
+  { TR, TJ, WR, cos_kernel<TR, TJ, WR> }
+const CosVariant kVariants[] = {
+    COS_V(4, 4, 1),  COS_V(4, 8, 1),  COS_V(4, 12, 1), COS_V(4, 16, 1), COS_V(4, 18, 1),
+    COS_V(2, 16, 2), COS_V(2, 18, 2),
+    COS_V(2, 16, 1), COS_V(2, 18, 1), COS_V(1, 16, 1),
+};
+
+// pick the strike-block width that wastes the fewest padded columns, then the largest row tile
+// whose shared-memory footprint fits
+const CosVariant* pick_variant(fop_handle_t h, int K, int J, int* nblk_out) {
+  int want_tr = 0, want_wr = 0;
+  if (const char* e = getenv("FOP_COS_VARIANT")) {  // tuning knob: "TR,WR", e.g. "2,2"
+    sscanf(e, "%d,%d", &want_tr, &want_wr);
+  }
+  const CosVariant* best = nullptr;
+  long long best_cost = 0;
+  int best_nblk = 0;
+  for (const CosVariant& v : kVariants) {
+    if (want_tr ? (v.TR != want_tr || v.WR != want_wr) : (v.WR != 1)) continue;
+    const CosSmem L = cos_smem_layout(K, v.TR, v.TJ, v.WR);
+    if (L.total > h->smem_optin) continue;
+    const int JB = 4 * v.TJ;
+    const int nblk = (J + JB - 1) / JB;
+    // padded columns, penalised by smaller row tiles (less reuse of the streamed basis)
+    const long long cost = (long long)nblk * JB * (v.TR == 4 ? 4 : v.TR == 2 ? 5 : 6);
+    if (!best || cost < best_cost || (cost == best_cost && JB > 4 * best->TJ)) {
+      best = &v;
+      best_cost = cost;
+      best_nblk = nblk;
+    }
+  }
+  *nblk_out = best_nblk;
+  return best;
+}
+
+// chiK / phiK of OptionPricing.h:284-300 with c = a = xMin, d = 0  (V_k = phi_k - chi_k, :342)
+double vk_put(double xMin, double u, int k) {
+  const double a = xMin, c = xMin, d = 0.0;
+  const double ed = std::exp(d), ec = std::exp(c);
+  const double chi = (std::cos(u * (d - a)) * ed - std::cos(u * (c - a)) * ec +
+                      u * std::sin(u * (d - a)) * ed - u * std::sin(u * (c - a)) * ec) /
+                     (1.0 + u * u);
+  const double phi = k == 0 ? d - c : (std::sin(u * (d - a)) - std::sin(u * (c - a))) / u;
+  return phi - chi;
+}
+
+int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, const double* K_desc,
+            int J, double S0, double r, const double* T, int M, int numU, int kind,
+            const double* mkt, const double* w, double* out, double* loss) {
+  if (!h) return FOP_INVALID_ARG;
+  const int np = num_params(model.base, model.time_change);
+  if (np == 0) return fail(h, FOP_INVALID_ARG, "unknown model (%d,%d)", model.base, model.time_change);
+  if (!params || !K_desc || !T) return fail(h, FOP_INVALID_ARG, "null input pointer");
+  if (!out && !loss) return fail(h, FOP_INVALID_ARG, "no output requested");
+  if (P < 0 || J < 2 || M < 1 || numU < 1 || numU > 1024 || kind < 0 || kind > 7)
+    return fail(h, FOP_INVALID_ARG, "bad sizes P=%d J=%d M=%d numU=%d kind=%d", P, J, M, numU, kind);
+  if (loss && !mkt) return fail(h, FOP_INVALID_ARG, "loss requested without market prices");
+  if (P == 0) return FOP_OK;
+  FOP_CUDA(h, cudaSetDevice(h->device));
+
+  int nblk = 0;
+  const CosVariant* v = pick_variant(h, numU, J, &nblk);
+  if (!v) return fail(h, FOP_UNSUPPORTED, "numU=%d does not fit in shared memory", numU);
+  const int JB = 4 * v->TJ, Jp = nblk * JB, R = cos_rows(v->TR, v->WR);
+
+  // small host-side tables (strike list may live on the device)
+  std::vector<double> Kh(J), Th(M);
+  FOP_CUDA(h, cudaMemcpy(Kh.data(), K_desc, sizeof(double) * J, cudaMemcpyDefault));
+  FOP_CUDA(h, cudaMemcpy(Th.data(), T, sizeof(double) * M, cudaMemcpyDefault));
+  std::vector<double> tab(2 * (size_t)numU + J);
+  double* uk = tab.data();
+  double* vk = uk + numU;
+  double* x = vk + numU;
+  for (int j = 0; j < J; ++j) x[j] = std::log(S0 / Kh[j]);  // getXFromK, OptionPricing.h:110-117
+  const double xMin = x[0], xMax = x[J - 1];
+  const double du = M_PI / (xMax - xMin), cp = 2.0 / (xMax - xMin);
+  for (int k = 0; k < numU; ++k) {
+    uk[k] = du * k;
+    vk[k] = vk_put(xMin, uk[k], k) * cp * (k == 0 ? 0.5 : 1.0);
+  }
+
+  const bool out_host = out && !is_device_ptr(out);
+  const bool loss_host = loss && !is_device_ptr(loss);
+  // process parameter sets in chunks so a host-bound price matrix never needs more than ~1 GiB
+  // of device staging
+  long long chunkP = P;
+  if (out_host) {
+    const long long per_set = (long long)M * J * 8;
+    chunkP = std::max<long long>(1, std::min<long long>(P, (1ll << 30) / per_set));
+  }
+  const long long chunk_rows = chunkP * M;
+
+  Arena ar(h);
+  size_t need = Arena::pad(tab.size() * 8) + Arena::pad((size_t)J * 8) + Arena::pad((size_t)M * 8) +
+                Arena::pad((size_t)2 * numU * Jp * 8) + stage_bytes(params, (size_t)P * np * 8);
+  if (mkt) need += stage_bytes(mkt, (size_t)M * J * 8);
+  if (w) need += stage_bytes(w, (size_t)M * J * 8);
+  if (out_host) need += Arena::pad((size_t)chunk_rows * J * 8);
+  if (loss) need += Arena::pad((size_t)P * M * 8) + (loss_host ? Arena::pad((size_t)P * 8) : 0);
+  FOP_TRY(ar.reserve(need));
+
+  double* d_tab = ar.alloc<double>(tab.size());
+  double* d_K = ar.alloc<double>(J);
+  double* d_T = ar.alloc<double>(M);
+  double* d_basis = ar.alloc<double>((size_t)2 * numU * Jp);
+  FOP_CUDA(h, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  FOP_CUDA(h, cudaMemcpyAsync(d_K, Kh.data(), (size_t)J * 8, cudaMemcpyHostToDevice, h->stream));
+  FOP_CUDA(h, cudaMemcpyAsync(d_T, Th.data(), (size_t)M * 8, cudaMemcpyHostToDevice, h->stream));
+  const double *d_params = nullptr, *d_mkt = nullptr, *d_w = nullptr;
+  FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
+  if (mkt) FOP_TRY(stage_in(h, ar, mkt, (size_t)M * J, &d_mkt));
+  if (w) FOP_TRY(stage_in(h, ar, w, (size_t)M * J, &d_w));
+  double* d_out_tmp = out_host ? ar.alloc<double>((size_t)chunk_rows * J) : nullptr;
+  double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M) : nullptr;
+  double* d_loss = loss ? (loss_host ? ar.alloc<double>(P) : loss) : nullptr;
+
+  {
+    const int n = numU * Jp;
+    cos_basis_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_tab, d_tab + 2 * numU, numU, J, Jp,
+                                                             d_basis);
+    FOP_LAUNCH_CHECK(h);
+  }
+  const CosSmem L = cos_smem_layout(numU, v->TR, v->TJ, v->WR);
+  FOP_CUDA(h, cudaFuncSetAttribute(v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)L.total));
+
+  for (long long p0 = 0; p0 < P; p0 += chunkP) {
+    const int pc = (int)std::min<long long>(chunkP, P - p0);
+    CosArgs a;
+    a.base = model.base;  a.tc = model.time_change;  a.greek = kind >> 1;  a.kind = kind;
+    a.P = pc;  a.M = M;  a.J = J;  a.K = numU;  a.Jp = Jp;  a.nblk = nblk;  a.np = np;
+    a.r = r;  a.S0 = S0;
+    a.params = d_params + (size_t)p0 * np;
+    a.T = d_T;  a.uk = d_tab;  a.vk = d_tab + numU;  a.basis = d_basis;  a.strikes = d_K;
+    a.out = out ? (out_host ? d_out_tmp : out + (size_t)p0 * M * J) : nullptr;
+    a.mkt = d_mkt;  a.w = d_w;
+    a.rowloss = loss ? d_rowloss + (size_t)p0 * M : nullptr;
+    const long long rows = (long long)pc * M;
+    const long long ntiles = (rows + R - 1) / R;
+    const int grid = (int)std::min<long long>(ntiles, h->sm_count);
+    v->kernel<<<grid, 256 * v->WR, L.total, h->stream>>>(a);
+    FOP_LAUNCH_CHECK(h);
+    if (out_host)
+      FOP_CUDA(h, cudaMemcpyAsync(out + (size_t)p0 * M * J, d_out_tmp, (size_t)rows * J * 8,
+                                  cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (loss) {
+    cos_loss_finalize_kernel<<<(P + 255) / 256, 256, 0, h->stream>>>(d_rowloss, P, M, J, d_loss);
+    FOP_LAUNCH_CHECK(h);
+    if (loss_host)
+      FOP_CUDA(h, cudaMemcpyAsync(loss, d_loss, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (out_host || loss_host) FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FOP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fop_cos(fop_handle_t h, fop_model_t model, const double* params, int P, const double* K_desc,
+            int J, double S0, double r, const double* T, int M, int numU, int kind, double* out) {
+  if (h && !out) return fop::fail(h, FOP_INVALID_ARG, "null output pointer");
+  return cos_run(h, model, params, P, K_desc, J, S0, r, T, M, numU, kind, nullptr, nullptr, out,
+                 nullptr);
+}
+
+int fop_cos_loss(fop_handle_t h, fop_model_t model, const double* params, int P,
+                 const double* K_desc, int J, double S0, double r, const double* T, int M,
+                 int numU, const double* mkt, const double* w, double* loss, double* prices_out) {
+  if (h && (!loss || !mkt)) return fop::fail(h, FOP_INVALID_ARG, "null loss / market pointer");
+  return cos_run(h, model, params, P, K_desc, J, S0, r, T, M, numU, FOP_CALL_PRICE, mkt, w,
+                 prices_out, loss);
+}
+
+}  // extern "C"

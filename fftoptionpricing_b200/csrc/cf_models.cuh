@@ -1,0 +1,178 @@
+// Characteristic-function library (device, fp64).
+//
+// Restates, as closed-set device functions, the CFs the reference builds from lambdas over the
+// un-vendored `chfunctions::` library (call sites test.cpp:54,570,731,887-905,
+// 1049-1058,1087-1096,1119; generateCharts.cpp:190-380):
+//   gaussLogCF(u,mu,s)          = u mu + s^2 u^2 / 2
+//   mertonLogRNCF(u,l,mJ,sJ,r,s)= gaussLogCF(u, r - s^2/2 - l(e^{mJ+sJ^2/2}-1), s) + l(e^{u mJ+sJ^2u^2/2}-1)
+//   cgmyLogRNCF(u,C,G,M,Y,r,s)  = gaussLogCF(u, r - s^2/2 - k(1), s) + k(u),
+//                                 k(u) = C Gamma(-Y)[(M-u)^Y + (G+u)^Y - M^Y - G^Y]  (0 if C == 0)
+//   cirLogMGF(psi,a,kap,sv,t,v0)= -b v0 - c, delta = sqrt(kap^2 + 2 psi sv^2), e = exp(-delta t),
+//                                 b = 2 psi (1-e)/(delta+kap+(delta-kap)e),
+//                                 c = (a/sv^2)[2 log(1-(delta-kap)(1-e)/(2 delta)) + (delta-kap) t]
+//                                 (sv == 0: deterministic clock, test.cpp:1187)
+//   time-changed CF             = exp(r T u + cirLogMGF(-psi_0(u), speed, speed - adaV rho u s, adaV, T, v0Hat))
+//
+// The evaluation is split in two so that each (parameter set, u) pair is worked out once and
+// re-used for every maturity: cf_prepare() does everything that does not depend on T (the Levy
+// exponent with its complex powers / exponentials, kappa(u), delta, ...), cf_log_at() the rest.
+#pragma once
+#include "cplx.cuh"
+
+namespace fop {
+
+enum { BASE_GAUSS = 0, BASE_MERTON = 1, BASE_CGMY = 2 };
+enum { TC_NONE = 0, TC_CIR = 1, TC_CIR_DIFFUSION = 2 };
+
+__host__ __device__ __forceinline__ int num_base_params(int base) {
+  return base == BASE_GAUSS ? 1 : base == BASE_MERTON ? 4 : base == BASE_CGMY ? 5 : 0;
+}
+__host__ __device__ __forceinline__ int num_params(int base, int tc) {
+  const int nb = num_base_params(base);
+  if (nb == 0 || tc < 0 || tc > 2) return 0;
+  return nb + (tc == TC_NONE ? 0 : 4);
+}
+
+// Per-parameter-set constants (everything that depends on theta only).
+struct ModelConsts {
+  double sigma, hs2;          // sigma, sigma^2/2
+  double comp;                // jump compensator per unit time: lambda(E e^J - 1) or k(1)
+  double lam, muJ, hsJ2;      // Merton
+  double cg, G, M, Y, myGy;   // CGMY: cg = C Gamma(-Y), myGy = M^Y + G^Y
+  double speed, adaV, v0, aos2, kap1;  // CIR: aos2 = speed/adaV^2, kappa(u) = speed - kap1 u
+};
+
+__device__ __forceinline__ void make_consts(int base, int tc, const double* __restrict__ p,
+                                            ModelConsts& c) {
+  c.sigma = p[0];
+  c.hs2 = 0.5 * p[0] * p[0];
+  c.comp = 0.0;
+  c.lam = c.muJ = c.hsJ2 = 0.0;
+  c.cg = c.G = c.M = c.Y = c.myGy = 0.0;
+  if (base == BASE_MERTON) {
+    c.lam = p[1];
+    c.muJ = p[2];
+    c.hsJ2 = 0.5 * p[3] * p[3];
+    c.comp = c.lam * (exp(c.muJ + c.hsJ2) - 1.0);
+  } else if (base == BASE_CGMY) {
+    const double C = p[1];
+    c.G = p[2];
+    c.M = p[3];
+    c.Y = p[4];
+    if (C != 0.0) {
+      c.cg = C * tgamma(-c.Y);
+      c.myGy = pow(c.M, c.Y) + pow(c.G, c.Y);
+      c.comp = c.cg * (pow(c.M - 1.0, c.Y) + pow(c.G + 1.0, c.Y) - c.myGy);
+    }
+  }
+  c.speed = c.adaV = c.v0 = c.aos2 = c.kap1 = 0.0;
+  if (tc != TC_NONE) {
+    const double* q = p + num_base_params(base);
+    c.speed = q[0];
+    c.adaV = q[1];
+    c.v0 = q[3];
+    c.kap1 = q[1] * q[2] * c.sigma;  // adaV * rho * sigma
+    c.aos2 = c.speed / (c.adaV * c.adaV);
+  }
+}
+
+// uncompensated jump exponent
+__device__ __forceinline__ cd jump_exponent(int base, const ModelConsts& c, cd u) {
+  if (base == BASE_MERTON) {
+    // lambda (exp(u muJ + sJ^2 u^2/2) - 1)
+    const cd uu = u * u;
+    const cd e = cexp(mk(u.x * c.muJ + c.hsJ2 * uu.x, u.y * c.muJ + c.hsJ2 * uu.y));
+    return mk(c.lam * (e.x - 1.0), c.lam * e.y);
+  }
+  if (base == BASE_CGMY) {
+    if (c.cg == 0.0) return mk(0.0, 0.0);
+    const cd a = cpow(mk(c.M - u.x, -u.y), c.Y);
+    const cd b = cpow(mk(c.G + u.x, u.y), c.Y);
+    return mk(c.cg * (a.x + b.x - c.myGy), c.cg * (a.y + b.y));
+  }
+  return mk(0.0, 0.0);
+}
+
+// risk-neutral Levy exponent per unit time: u (rate - s2 - comp) + s2 u^2 + jumps(u),
+// s2 = sigma^2/2 (or 0 when the diffusion is switched off)
+__device__ __forceinline__ cd levy_exponent(int base, const ModelConsts& c, cd u, double rate,
+                                            double s2, bool with_jumps) {
+  const double mu = rate - s2 - (with_jumps ? c.comp : 0.0);
+  const cd uu = u * u;
+  cd r = mk(u.x * mu + s2 * uu.x, u.y * mu + s2 * uu.y);
+  if (with_jumps && base != BASE_GAUSS) r = r + jump_exponent(base, c, u);
+  return r;
+}
+
+// T-independent part of log phi(u)
+struct CfPre {
+  cd lin;    // log phi += lin * T
+  cd pod;    // psi/delta            (adaV == 0: psi)
+  cd dmk;    // delta - kappa
+  cd g;      // (delta-kappa)/(2 delta)
+  cd delta;  //                       (adaV == 0: kappa)
+};
+
+__device__ __forceinline__ void cf_prepare(int base, int tc, const ModelConsts& c, cd u, double r,
+                                           CfPre& pre) {
+  if (tc == TC_NONE) {
+    pre.lin = levy_exponent(base, c, u, r, c.hs2, true);
+    return;
+  }
+  cd psi;  // argument of cirLogMGF = -(time-changed exponent with r = 0)
+  if (tc == TC_CIR) {
+    psi = -levy_exponent(base, c, u, 0.0, c.hs2, true);
+    pre.lin = mk(r * u.x, r * u.y);
+  } else {  // only the diffusion is time changed; jumps (compensated, sigma = 0) in calendar time
+    psi = -levy_exponent(BASE_GAUSS, c, u, 0.0, c.hs2, false);
+    pre.lin = mk(r * u.x, r * u.y) + levy_exponent(base, c, u, 0.0, 0.0, true);
+  }
+  const cd kap = mk(c.speed - c.kap1 * u.x, -c.kap1 * u.y);
+  if (c.adaV == 0.0) {
+    pre.pod = psi;
+    pre.delta = kap;
+    return;
+  }
+  const double s2v = 2.0 * c.adaV * c.adaV;
+  const cd kk = kap * kap;
+  const cd delta = csqrt(mk(kk.x + s2v * psi.x, kk.y + s2v * psi.y));
+  pre.delta = delta;
+  pre.dmk = delta - kap;
+  pre.g = cdiv(pre.dmk, mk(2.0 * delta.x, 2.0 * delta.y));
+  pre.pod = cdiv(psi, delta);
+}
+
+// log phi(u) at maturity T
+__device__ __forceinline__ cd cf_log_at(int tc, const ModelConsts& c, const CfPre& pre, double T) {
+  cd l = mk(pre.lin.x * T, pre.lin.y * T);
+  if (tc == TC_NONE) return l;
+  if (c.adaV == 0.0) {
+    const cd kp = pre.delta, ps = pre.pod;
+    const cd ek = 1.0 - cexp(mk(-kp.x * T, -kp.y * T));
+    const cd ekk = cdiv(ek, kp);
+    const cd b = ps * ekk;
+    const cd cc = cdiv(mk(c.speed * ps.x, c.speed * ps.y), kp) * (T - ekk);
+    return l - (c.v0 * b) - cc;
+  }
+  const cd e = cexp(mk(-pre.delta.x * T, -pre.delta.y * T));
+  const cd ome = 1.0 - e;
+  const cd w = 1.0 - pre.g * ome;
+  const cd b = pre.pod * cdiv(ome, w);
+  const cd lw = clog(w);
+  const cd cc = mk(c.aos2 * (2.0 * lw.x + pre.dmk.x * T), c.aos2 * (2.0 * lw.y + pre.dmk.y * T));
+  return l - (c.v0 * b) - cc;
+}
+
+// Option transforms applied to phi(u) (OptionPricing.h:44-73): 0 price, 1 delta, 2 gamma, 3 theta
+__device__ __forceinline__ cd option_transform(int greek, cd phi, cd u, double r) {
+  if (greek == 0) return phi;
+  if (greek == 1) return phi * u;
+  if (greek == 2) return -(phi * (u * (1.0 - u)));
+  if (phi.x > 0.0) {  // theta; log of the CF VALUE (principal branch), as the reference does
+    const cd l = clog(phi);
+    return -(mk(l.x - r, l.y) * phi);
+  }
+  return mk(0.0, 0.0);
+}
+
+}  // namespace fop

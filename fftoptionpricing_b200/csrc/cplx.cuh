@@ -1,0 +1,76 @@
+// fp64 complex helpers for device code.  Principal branches match libstdc++'s std::complex
+// (sqrt, log, pow(complex, real)), which is what the reference's characteristic functions use
+// (SURVEY.md "Hard parts": replicate, don't improve).  No fast-math anywhere.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace fop {
+
+struct cd {
+  double x, y;
+};
+
+__host__ __device__ __forceinline__ cd mk(double x, double y) { cd r; r.x = x; r.y = y; return r; }
+__host__ __device__ __forceinline__ cd operator+(cd a, cd b) { return mk(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cd operator-(cd a, cd b) { return mk(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cd operator-(cd a) { return mk(-a.x, -a.y); }
+__host__ __device__ __forceinline__ cd operator*(cd a, cd b) {
+  return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cd operator*(double s, cd a) { return mk(s * a.x, s * a.y); }
+__host__ __device__ __forceinline__ cd operator*(cd a, double s) { return mk(s * a.x, s * a.y); }
+__host__ __device__ __forceinline__ cd operator+(cd a, double s) { return mk(a.x + s, a.y); }
+__host__ __device__ __forceinline__ cd operator+(double s, cd a) { return mk(a.x + s, a.y); }
+__host__ __device__ __forceinline__ cd operator-(cd a, double s) { return mk(a.x - s, a.y); }
+__host__ __device__ __forceinline__ cd operator-(double s, cd a) { return mk(s - a.x, -a.y); }
+__host__ __device__ __forceinline__ cd conj(cd a) { return mk(a.x, -a.y); }
+__host__ __device__ __forceinline__ double norm(cd a) { return a.x * a.x + a.y * a.y; }
+
+__host__ __device__ __forceinline__ cd cdiv(cd a, cd b) {
+  const double inv = 1.0 / (b.x * b.x + b.y * b.y);
+  return mk((a.x * b.x + a.y * b.y) * inv, (a.y * b.x - a.x * b.y) * inv);
+}
+__host__ __device__ __forceinline__ cd cdiv(cd a, double s) { return mk(a.x / s, a.y / s); }
+
+__device__ __forceinline__ cd cexp(cd z) {
+  const double e = exp(z.x);
+  double s, c;
+  sincos(z.y, &s, &c);
+  return mk(e * c, e * s);
+}
+// e^{i t}
+__device__ __forceinline__ cd cis(double t) {
+  double s, c;
+  sincos(t, &s, &c);
+  return mk(c, s);
+}
+// principal log: Im in (-pi, pi]
+__device__ __forceinline__ cd clog(cd z) {
+  return mk(0.5 * log(z.x * z.x + z.y * z.y), atan2(z.y, z.x));
+}
+// principal square root (Re >= 0; on the negative real axis the sign of Im follows the sign of z.y)
+__device__ __forceinline__ cd csqrt(cd z) {
+  if (z.x == 0.0 && z.y == 0.0) return mk(0.0, z.y);
+  const double r = sqrt(z.x * z.x + z.y * z.y);
+  if (z.x >= 0.0) {
+    const double t = sqrt(0.5 * (r + z.x));
+    return mk(t, z.y / (2.0 * t));
+  }
+  const double t = sqrt(0.5 * (r - z.x));
+  return mk(fabs(z.y) / (2.0 * t), copysign(t, z.y));
+}
+// pow(complex, real) with libstdc++ semantics: real positive base -> real pow; 0 -> 0 (needed by
+// the reference's own CGMY Carr-Madan test where (M - u) is exactly 0 at omega = 0,
+// test.cpp:841 with alpha + 1 = 2.5 = M); otherwise polar(exp(y log|z|), y arg z).
+__device__ __forceinline__ cd cpow(cd z, double y) {
+  if (z.y == 0.0 && z.x > 0.0) return mk(pow(z.x, y), 0.0);
+  if (z.x == 0.0 && z.y == 0.0) return mk(0.0, 0.0);
+  const cd l = clog(z);
+  const double m = exp(y * l.x);
+  double s, c;
+  sincos(y * l.y, &s, &c);
+  return mk(m * c, m * s);
+}
+
+}  // namespace fop

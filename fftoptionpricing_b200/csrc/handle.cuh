@@ -1,0 +1,117 @@
+// Handle, error plumbing and buffer staging shared by every C-ABI translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fftop_b200.h"
+
+struct fop_handle_s {
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  // bump arena for per-call device temporaries (grown on demand, reused across calls)
+  unsigned char* arena = nullptr;
+  size_t arena_cap = 0, arena_used = 0;
+  // cached twiddle tables: tw[N] holds e^{-2 pi i k/N}, k < N  (see fft_smem.cuh)
+  struct Twiddle { int N; double2* d; };
+  std::vector<Twiddle> twiddles;
+};
+
+namespace fop {
+
+inline int fail(fop_handle_t h, int status, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return status;
+}
+
+#define FOP_CUDA(h, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return fop::fail(h, e__ == cudaErrorMemoryAllocation ? FOP_OOM : FOP_CUDA_ERROR,     \
+                       "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,  \
+                       __LINE__);                                                          \
+  } while (0)
+
+inline bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// Per-call arena.  begin() resets the bump pointer; reserve() must be called before any alloc()
+// of the call with the total (so the arena never moves while kernels are queued on it).
+struct Arena {
+  fop_handle_t h;
+  explicit Arena(fop_handle_t hh) : h(hh) { h->arena_used = 0; }
+  static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+  int reserve(size_t total) {
+    total += 4096;
+    if (total <= h->arena_cap) return FOP_OK;
+    FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->arena) cudaFree(h->arena);
+    h->arena = nullptr;
+    h->arena_cap = 0;
+    FOP_CUDA(h, cudaMalloc(&h->arena, total));
+    h->arena_cap = total;
+    return FOP_OK;
+  }
+  template <typename T>
+  T* alloc(size_t count) {
+    const size_t b = pad(count * sizeof(T));
+    if (h->arena_used + b > h->arena_cap) return nullptr;
+    T* p = reinterpret_cast<T*>(h->arena + h->arena_used);
+    h->arena_used += b;
+    return p;
+  }
+};
+
+// returns a device pointer for a read-only input (copies host data on the handle's stream)
+template <typename T>
+inline int stage_in(fop_handle_t h, Arena& ar, const T* src, size_t count, const T** dev) {
+  if (is_device_ptr(src)) {
+    *dev = src;
+    return FOP_OK;
+  }
+  T* d = ar.alloc<T>(count);
+  if (!d) return fail(h, FOP_OOM, "arena exhausted staging %zu bytes", count * sizeof(T));
+  FOP_CUDA(h, cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  *dev = d;
+  return FOP_OK;
+}
+inline size_t stage_bytes(const void* src, size_t bytes) {
+  return is_device_ptr(src) ? 0 : Arena::pad(bytes);
+}
+
+#define FOP_TRY(expr)              \
+  do {                             \
+    int st__ = (expr);             \
+    if (st__ != FOP_OK) return st__; \
+  } while (0)
+
+#define FOP_LAUNCH_CHECK(h)                                                               \
+  do {                                                                                    \
+    (h)->launches++;                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess)                                                               \
+      return fop::fail(h, FOP_CUDA_ERROR, "kernel launch failed: %s (%s:%d)",             \
+                       cudaGetErrorString(e__), __FILE__, __LINE__);                      \
+  } while (0)
+
+}  // namespace fop

@@ -1,0 +1,222 @@
+"""Host-side mirror of the reference's pricing / calibration interface over the C ABI.
+
+``Engine`` owns one ``fop_handle_t`` (one GPU, one stream).  Its methods take numpy arrays (host
+buffers, copied inside the call) or torch CUDA tensors / raw device pointers (no copies, work is
+only enqueued) and have the same signatures as ``oracle.oracle.Oracle`` so that parity tests call
+both sides identically.  The reference-named entry points (``CarrMadanCall``,
+``FangOostCallPrice``, ``FSTSPrice``, ``getObjFn_arr`` ...) live in ``pricing.py`` /
+``calibration.py`` on top of this class.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+GAUSS, MERTON, CGMY = 0, 1, 2
+TC_NONE, TC_CIR, TC_CIR_DIFFUSION = 0, 1, 2
+CALL_PRICE, PUT_PRICE, CALL_DELTA, PUT_DELTA, CALL_GAMMA, PUT_GAMMA, CALL_THETA, PUT_THETA = range(8)
+FSTS_PRICE, FSTS_DELTA, FSTS_GAMMA, FSTS_THETA = range(4)
+PAYOFF_CALL, PAYOFF_PUT = 0, 1
+
+
+class FopError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"fftop_b200 status {status}: {message}")
+        self.status = status
+
+
+def num_params(base: int, tc: int) -> int:
+    return int(_lib.load_library().fop_model_num_params(_lib.fop_model_t(base, tc)))
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _Buf:
+    """Pointer + keep-alive for an argument that is a numpy array, torch tensor or None."""
+
+    def __init__(self, x, dtype=np.float64, shape=None, writable=False):
+        self.keep = None
+        self.ptr = None
+        self.is_device = False
+        if x is None:
+            return
+        if _is_torch(x):
+            import torch
+            assert x.dtype == (torch.float64 if dtype == np.float64 else torch.complex128), x.dtype
+            assert x.is_contiguous()
+            self.keep = x
+            self.ptr = C.c_void_p(x.data_ptr())
+            self.is_device = x.is_cuda
+            self.size = x.numel()
+            return
+        a = np.asarray(x, dtype=dtype)
+        if writable:
+            assert a.flags.c_contiguous and a.flags.writeable
+        else:
+            a = np.ascontiguousarray(a)
+        if shape is not None:
+            a = a.reshape(shape)
+        self.keep = a
+        self.ptr = C.c_void_p(a.ctypes.data)
+        self.size = a.size
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._L = _lib.load_library()
+        h = C.c_void_p()
+        st = self._L.fop_create(C.byref(h), int(device))
+        if st != 0:
+            raise FopError(st, "fop_create failed: no usable CUDA device "
+                               f"{device} (this library has no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.fop_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st: int):
+        if st != 0:
+            raise FopError(st, self._L.fop_last_error(self._h).decode())
+
+    @property
+    def stream_ptr(self) -> int:
+        return int(self._L.fop_get_stream(self._h) or 0)
+
+    def synchronize(self):
+        self._check(self._L.fop_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.fop_launch_count(self._h))
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double()
+        self._check(self._L.fop_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def microbench_fp64(self):
+        v = (C.c_double * 4)()
+        self._check(self._L.fop_microbench_fp64(self._h, v))
+        return list(v)
+
+    @staticmethod
+    def _params(base, tc, params):
+        np_ = num_params(base, tc)
+        if np_ == 0:
+            raise FopError(1, f"unknown model ({base},{tc})")
+        if _is_torch(params):
+            assert params.numel() % np_ == 0
+            return _Buf(params), params.numel() // np_
+        p = np.ascontiguousarray(np.asarray(params, dtype=np.float64)).reshape(-1, np_)
+        return _Buf(p), p.shape[0]
+
+    @staticmethod
+    def _out(out, shape):
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        b = _Buf(out, writable=True)
+        assert b.size == int(np.prod(shape)), (b.size, shape)
+        return out, b
+
+    # ------------------------------------------------------------------ pricers
+    def carr_madan(self, base, tc, params, N, ada, alpha, S0, r, T, is_put=False, out=None):
+        pb, P = self._params(base, tc, params)
+        out, ob = self._out(out, (P, N))
+        self._check(self._L.fop_carr_madan(self._h, _lib.fop_model_t(base, tc), pb.ptr, P, int(N),
+                                           float(ada), float(alpha), float(S0), float(r), float(T),
+                                           int(bool(is_put)), ob.ptr))
+        return out
+
+    def cos(self, base, tc, params, K_desc, S0, r, T: Sequence[float], numU, kind=0, out=None):
+        pb, P = self._params(base, tc, params)
+        Kb = _Buf(K_desc)
+        Tb = _Buf(T if _is_torch(T) else np.atleast_1d(np.asarray(T, dtype=np.float64)))
+        out, ob = self._out(out, (P, Tb.size, Kb.size))
+        self._check(self._L.fop_cos(self._h, _lib.fop_model_t(base, tc), pb.ptr, P, Kb.ptr, Kb.size,
+                                    float(S0), float(r), Tb.ptr, Tb.size, int(numU), int(kind),
+                                    ob.ptr))
+        return out
+
+    def fsts(self, base, tc, params, N, xmax, strike, r, T, steps=1, american=False, payoff=0,
+             kind=0, out=None):
+        pb, P = self._params(base, tc, params)
+        out, ob = self._out(out, (P, N))
+        self._check(self._L.fop_fsts(self._h, _lib.fop_model_t(base, tc), pb.ptr, P, int(N),
+                                     float(xmax), float(strike), float(r), float(T), int(steps),
+                                     int(bool(american)), int(payoff), int(kind), ob.ptr))
+        return out
+
+    def objfn_cf(self, base, tc, params, u, phiHat, r, T, out=None):
+        pb, P = self._params(base, tc, params)
+        ub = _Buf(u)
+        if _is_torch(phiHat):
+            phb = _Buf(phiHat, dtype=np.complex128)
+        else:
+            ph = np.ascontiguousarray(np.asarray(phiHat, dtype=np.complex128)).view(np.float64)
+            phb = _Buf(ph)
+        out, ob = self._out(out, (P,))
+        self._check(self._L.fop_objfn_cf(self._h, _lib.fop_model_t(base, tc), pb.ptr, P, ub.ptr,
+                                         phb.ptr, ub.size, float(r), float(T), ob.ptr))
+        return out
+
+    def cos_loss(self, base, tc, params, K_desc, S0, r, T, numU, mkt, w=None, want_prices=False,
+                 out=None, prices_out=None):
+        pb, P = self._params(base, tc, params)
+        Kb = _Buf(K_desc)
+        Tb = _Buf(T if _is_torch(T) else np.atleast_1d(np.asarray(T, dtype=np.float64)))
+        mb, wb = _Buf(mkt), _Buf(w)
+        assert mb.size == Tb.size * Kb.size
+        out, ob = self._out(out, (P,))
+        pr, prb = (None, _Buf(None))
+        if want_prices or prices_out is not None:
+            pr, prb = self._out(prices_out, (P, Tb.size, Kb.size))
+        self._check(self._L.fop_cos_loss(self._h, _lib.fop_model_t(base, tc), pb.ptr, P, Kb.ptr,
+                                         Kb.size, float(S0), float(r), Tb.ptr, Tb.size, int(numU),
+                                         mb.ptr, wb.ptr, ob.ptr, prb.ptr))
+        return (out, pr) if want_prices else out
+
+    def fft(self, x, inverse=False):
+        """Unnormalised batched FFT over the last axis (fft.hpp:49-61).  numpy in -> numpy out
+        (copy); a torch CUDA complex128 tensor is transformed in place."""
+        if _is_torch(x):
+            N = x.shape[-1]
+            b = _Buf(x, dtype=np.complex128)
+            self._check(self._L.fop_fft(self._h, b.ptr, x.numel() // N, N, int(bool(inverse))))
+            return x
+        z = np.array(x, dtype=np.complex128, order="C", copy=True)
+        N = z.shape[-1]
+        self._check(self._L.fop_fft(self._h, C.c_void_p(z.ctypes.data), z.size // N, N,
+                                    int(bool(inverse))))
+        return z
+
+    # ------------------------------------------------------------------ grids (host)
+    def carr_madan_strikes(self, N, ada, S0):
+        out = np.empty(N)
+        self._L.fop_carr_madan_strikes(N, ada, S0, out.ctypes.data_as(_lib._dp))
+        return out
+
+    def fang_oost_strikes(self, xMin, xMax, S0, numX):
+        out = np.empty(numX)
+        self._L.fop_fang_oost_strikes(xMin, xMax, S0, numX, out.ctypes.data_as(_lib._dp))
+        return out
+
+    def strike_underlying(self, xMin, xMax, K, numX):
+        out = np.empty(numX)
+        self._L.fop_strike_underlying(xMin, xMax, K, numX, out.ctypes.data_as(_lib._dp))
+        return out
