@@ -4,7 +4,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "cos_kernels.cuh"
+#include "cos_split_kernels.cuh"
 #include "handle.cuh"
 
 namespace {
@@ -21,6 +21,29 @@ const CosVariant kVariants[] = {
     COS_V(2, 16, 2), COS_V(2, 18, 2),
     COS_V(2, 16, 1), COS_V(2, 18, 1), COS_V(1, 16, 1),
 };
+
+struct GemmVariant {
+  int TJ;
+  void (*kernel)(const CosGemmArgs);
+};
+const GemmVariant kGemm[] = {{4, cos_gemm_kernel<4>},   {8, cos_gemm_kernel<8>},
+                             {12, cos_gemm_kernel<12>}, {16, cos_gemm_kernel<16>},
+                             {18, cos_gemm_kernel<18>}};
+// strike-block width that wastes the fewest padded columns (ties -> wider block)
+const GemmVariant* pick_gemm(int J, int* nblk_out) {
+  const GemmVariant* best = nullptr;
+  long long best_cost = 0;
+  for (const GemmVariant& v : kGemm) {
+    const int JB = 4 * v.TJ, nblk = (J + JB - 1) / JB;
+    const long long cost = (long long)nblk * JB;
+    if (!best || cost < best_cost || (cost == best_cost && v.TJ > best->TJ)) {
+      best = &v;
+      best_cost = cost;
+      *nblk_out = nblk;
+    }
+  }
+  return best;
+}
 
 // pick the strike-block width that wastes the fewest padded columns, then the largest row tile
 // whose shared-memory footprint fits
@@ -75,10 +98,20 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   if (P == 0) return FOP_OK;
   FOP_CUDA(h, cudaSetDevice(h->device));
 
+  const bool fused = getenv("FOP_COS_FUSED") != nullptr;  // A/B knob: single fused kernel
   int nblk = 0;
-  const CosVariant* v = pick_variant(h, numU, J, &nblk);
-  if (!v) return fail(h, FOP_UNSUPPORTED, "numU=%d does not fit in shared memory", numU);
-  const int JB = 4 * v->TJ, Jp = nblk * JB, R = cos_rows(v->TR, v->WR);
+  const CosVariant* v = nullptr;
+  const GemmVariant* gv = nullptr;
+  int TJ = 0;
+  if (fused) {
+    v = pick_variant(h, numU, J, &nblk);
+    if (!v) return fail(h, FOP_UNSUPPORTED, "numU=%d does not fit in shared memory", numU);
+    TJ = v->TJ;
+  } else {
+    gv = pick_gemm(J, &nblk);
+    TJ = gv->TJ;
+  }
+  const int JB = 4 * TJ, Jp = nblk * JB, KK = 2 * numU;
 
   // small host-side tables (strike list may live on the device)
   std::vector<double> Kh(J), Th(M);
@@ -98,28 +131,28 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
 
   const bool out_host = out && !is_device_ptr(out);
   const bool loss_host = loss && !is_device_ptr(loss);
-  // process parameter sets in chunks so a host-bound price matrix never needs more than ~1 GiB
-  // of device staging
+  // Parameter sets are processed in chunks: bounds the coefficient matrix C (4 KiB per row at
+  // numU = 256) and the staging of a host-bound price matrix to ~1 GiB each.
   long long chunkP = P;
-  if (out_host) {
-    const long long per_set = (long long)M * J * 8;
-    chunkP = std::max<long long>(1, std::min<long long>(P, (1ll << 30) / per_set));
-  }
+  if (!fused) chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * KK * 8)));
+  if (out_host) chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * J * 8)));
   const long long chunk_rows = chunkP * M;
+  const int lossblk = fused ? 1 : nblk;
 
   Arena ar(h);
   size_t need = Arena::pad(tab.size() * 8) + Arena::pad((size_t)J * 8) + Arena::pad((size_t)M * 8) +
-                Arena::pad((size_t)2 * numU * Jp * 8) + stage_bytes(params, (size_t)P * np * 8);
+                Arena::pad((size_t)KK * Jp * 8) + stage_bytes(params, (size_t)P * np * 8);
   if (mkt) need += stage_bytes(mkt, (size_t)M * J * 8);
   if (w) need += stage_bytes(w, (size_t)M * J * 8);
+  if (!fused) need += Arena::pad((size_t)chunk_rows * KK * 8);
   if (out_host) need += Arena::pad((size_t)chunk_rows * J * 8);
-  if (loss) need += Arena::pad((size_t)P * M * 8) + (loss_host ? Arena::pad((size_t)P * 8) : 0);
+  if (loss) need += Arena::pad((size_t)P * M * lossblk * 8) + (loss_host ? Arena::pad((size_t)P * 8) : 0);
   FOP_TRY(ar.reserve(need));
 
   double* d_tab = ar.alloc<double>(tab.size());
   double* d_K = ar.alloc<double>(J);
   double* d_T = ar.alloc<double>(M);
-  double* d_basis = ar.alloc<double>((size_t)2 * numU * Jp);
+  double* d_basis = ar.alloc<double>((size_t)KK * Jp);
   FOP_CUDA(h, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
   FOP_CUDA(h, cudaMemcpyAsync(d_K, Kh.data(), (size_t)J * 8, cudaMemcpyHostToDevice, h->stream));
   FOP_CUDA(h, cudaMemcpyAsync(d_T, Th.data(), (size_t)M * 8, cudaMemcpyHostToDevice, h->stream));
@@ -127,8 +160,9 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
   if (mkt) FOP_TRY(stage_in(h, ar, mkt, (size_t)M * J, &d_mkt));
   if (w) FOP_TRY(stage_in(h, ar, w, (size_t)M * J, &d_w));
+  double* d_C = fused ? nullptr : ar.alloc<double>((size_t)chunk_rows * KK);
   double* d_out_tmp = out_host ? ar.alloc<double>((size_t)chunk_rows * J) : nullptr;
-  double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M) : nullptr;
+  double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M * lossblk) : nullptr;
   double* d_loss = loss ? (loss_host ? ar.alloc<double>(P) : loss) : nullptr;
 
   {
@@ -137,32 +171,64 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
                                                              d_basis);
     FOP_LAUNCH_CHECK(h);
   }
-  const CosSmem L = cos_smem_layout(numU, v->TR, v->TJ, v->WR);
-  FOP_CUDA(h, cudaFuncSetAttribute(v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)L.total));
+  CosSmem L{};
+  size_t gemm_smem = 0;
+  if (fused) {
+    L = cos_smem_layout(numU, v->TR, v->TJ, v->WR);
+    FOP_CUDA(h, cudaFuncSetAttribute(v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  } else {
+    gemm_smem = cos_gemm_smem(TJ);
+    FOP_CUDA(h, cudaFuncSetAttribute(gv->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+  }
 
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
     const int pc = (int)std::min<long long>(chunkP, P - p0);
-    CosArgs a;
-    a.base = model.base;  a.tc = model.time_change;  a.greek = kind >> 1;  a.kind = kind;
-    a.P = pc;  a.M = M;  a.J = J;  a.K = numU;  a.Jp = Jp;  a.nblk = nblk;  a.np = np;
-    a.r = r;  a.S0 = S0;
-    a.params = d_params + (size_t)p0 * np;
-    a.T = d_T;  a.uk = d_tab;  a.vk = d_tab + numU;  a.basis = d_basis;  a.strikes = d_K;
-    a.out = out ? (out_host ? d_out_tmp : out + (size_t)p0 * M * J) : nullptr;
-    a.mkt = d_mkt;  a.w = d_w;
-    a.rowloss = loss ? d_rowloss + (size_t)p0 * M : nullptr;
     const long long rows = (long long)pc * M;
-    const long long ntiles = (rows + R - 1) / R;
-    const int grid = (int)std::min<long long>(ntiles, h->sm_count);
-    v->kernel<<<grid, 256 * v->WR, L.total, h->stream>>>(a);
-    FOP_LAUNCH_CHECK(h);
+    double* out_here = out ? (out_host ? d_out_tmp : out + (size_t)p0 * M * J) : nullptr;
+    if (fused) {
+      CosArgs a;
+      a.base = model.base;  a.tc = model.time_change;  a.greek = kind >> 1;  a.kind = kind;
+      a.P = pc;  a.M = M;  a.J = J;  a.K = numU;  a.Jp = Jp;  a.nblk = nblk;  a.np = np;
+      a.r = r;  a.S0 = S0;
+      a.params = d_params + (size_t)p0 * np;
+      a.T = d_T;  a.uk = d_tab;  a.vk = d_tab + numU;  a.basis = d_basis;  a.strikes = d_K;
+      a.out = out_here;
+      a.mkt = d_mkt;  a.w = d_w;
+      a.rowloss = loss ? d_rowloss + (size_t)p0 * M : nullptr;
+      const int R = cos_rows(v->TR, v->WR);
+      const long long ntiles = (rows + R - 1) / R;
+      const int grid = (int)std::min<long long>(ntiles, h->sm_count);
+      v->kernel<<<grid, 256 * v->WR, L.total, h->stream>>>(a);
+      FOP_LAUNCH_CHECK(h);
+    } else {
+      CosCoeffArgs ca;
+      ca.base = model.base;  ca.tc = model.time_change;  ca.greek = kind >> 1;
+      ca.P = pc;  ca.M = M;  ca.K = numU;  ca.np = np;
+      ca.spb = std::max(1, std::min(COEFF_MAX_SPB, 1024 / numU));
+      ca.r = r;
+      ca.params = d_params + (size_t)p0 * np;
+      ca.T = d_T;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = d_C;
+      const int ngroups = (pc + ca.spb - 1) / ca.spb;
+      const int cgrid = std::min(ngroups, h->sm_count * 32);
+      if (M >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
+      else cos_coeff_kernel<1><<<cgrid, 256, 0, h->stream>>>(ca);
+      FOP_LAUNCH_CHECK(h);
+      CosGemmArgs ga;
+      ga.kind = kind;  ga.M = M;  ga.J = J;  ga.KK = KK;  ga.Jp = Jp;  ga.nblk = nblk;
+      ga.rows = rows;  ga.r = r;  ga.S0 = S0;
+      ga.C = d_C;  ga.basis = d_basis;  ga.T = d_T;  ga.strikes = d_K;
+      ga.out = out_here;  ga.mkt = d_mkt;  ga.w = d_w;
+      ga.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
+      const dim3 ggrid((unsigned)((rows + GEMM_RT - 1) / GEMM_RT), (unsigned)nblk);
+      gv->kernel<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
+      FOP_LAUNCH_CHECK(h);
+    }
     if (out_host)
       FOP_CUDA(h, cudaMemcpyAsync(out + (size_t)p0 * M * J, d_out_tmp, (size_t)rows * J * 8,
                                   cudaMemcpyDeviceToHost, h->stream));
   }
   if (loss) {
-    cos_loss_finalize_kernel<<<(P + 255) / 256, 256, 0, h->stream>>>(d_rowloss, P, M, J, d_loss);
+    cos_loss_finalize2_kernel<<<(P + 255) / 256, 256, 0, h->stream>>>(d_rowloss, P, M, J, lossblk, d_loss);
     FOP_LAUNCH_CHECK(h);
     if (loss_host)
       FOP_CUDA(h, cudaMemcpyAsync(loss, d_loss, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));

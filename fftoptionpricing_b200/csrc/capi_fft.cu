@@ -1,0 +1,235 @@
+// C ABI: fop_fft, fop_carr_madan  (include/fftop_b200.h)
+#include <algorithm>
+#include <cmath>
+
+#include "cf_models.cuh"
+#include "fft_engine.cuh"
+#include "handle.cuh"
+
+namespace {
+using namespace fop;
+
+int ilog2(int N) {
+  int n = 0;
+  while ((1 << n) < N) ++n;
+  return n;
+}
+
+}  // namespace
+namespace fop {
+// cached exact twiddle table e^{-2 pi i k/N} (also used by capi_fsts.cu)
+int get_twiddles_shared(fop_handle_t h, int N, const double2** out) {
+  for (auto& t : h->twiddles)
+    if (t.N == N) {
+      *out = t.d;
+      return FOP_OK;
+    }
+  double2* d = nullptr;
+  FOP_CUDA(h, cudaMalloc(&d, sizeof(double2) * (size_t)N));
+  twiddle_table_kernel<<<(N + 255) / 256, 256, 0, h->stream>>>(d, N);
+  FOP_LAUNCH_CHECK(h);
+  h->twiddles.push_back({N, d});
+  *out = d;
+  return FOP_OK;
+}
+}  // namespace fop
+namespace {
+inline int get_twiddles(fop_handle_t h, int N, const double2** out) { return fop::get_twiddles_shared(h, N, out); }
+
+// ---- generic load / store functors (fop_fft)
+struct LoadGen {
+  static constexpr size_t aux_bytes = 0;
+  const cd* data;
+  int N;
+  __device__ void prepare(void*, int, int) const {}
+  __device__ cd operator()(const void*, int, int p, int j) const { return data[(size_t)p * N + j]; }
+};
+struct StoreEpi {
+  cd* data;
+  int N;
+  __device__ void operator()(int p, int k, cd v) const { data[(size_t)p * N + k] = v; }
+};
+// direct O(N^2) transform for N < 16 (one thread per output)
+__global__ void tiny_dft_kernel(cd* data, int batch, int N, int sign) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch) return;
+  cd x[8], y[8];
+  for (int j = 0; j < N; ++j) x[j] = data[(size_t)idx * N + j];
+  for (int k = 0; k < N; ++k) {
+    cd acc = mk(0.0, 0.0);
+    for (int j = 0; j < N; ++j) {
+      double s, c;
+      sincospi(sign * 2.0 * (double)((j * k) % N) / (double)N, &s, &c);
+      acc = acc + x[j] * mk(c, s);
+    }
+    y[k] = acc;
+  }
+  for (int k = 0; k < N; ++k) data[(size_t)idx * N + k] = y[k];
+}
+
+// ---- Carr-Madan functors (OptionPricing.h:564-567 CallAug, :582-607 CarrMadanGeneric)
+struct CmGen {
+  static constexpr int MAX_SETS = 256;  // >= transforms per CTA of the single-CTA engine
+  static constexpr size_t aux_bytes = sizeof(ModelConsts) * MAX_SETS;
+  int base, tc, np;
+  const double* params;
+  double r, T, ada, alpha, discount, b;
+  __device__ void prepare(void* aux, int p0, int count) const {
+    ModelConsts* mc = reinterpret_cast<ModelConsts*>(aux);
+    if ((int)threadIdx.x < count) make_consts(base, tc, params + (size_t)(p0 + threadIdx.x) * np, mc[threadIdx.x]);
+    __syncthreads();
+  }
+  // x_j = discount * phi(v + alpha + 1) / (alpha^2 + alpha + v^2 + (2 alpha + 1) v) * e^{i b j ada}
+  //       * (3 -+ 1),  v = i j ada;  x_0 halved            (OptionPricing.h:594-599)
+  __device__ cd operator()(const void* aux, int p0, int p, int j) const {
+    const ModelConsts& mc = reinterpret_cast<const ModelConsts*>(aux)[p - p0];
+    const double w = j * ada;
+    const cd u = mk(alpha + 1.0, w);
+    CfPre pre;
+    cf_prepare(base, tc, mc, u, r, pre);
+    const cd phi = cexp(cf_log_at(tc, mc, pre, T));
+    const cd den = mk(alpha * alpha + alpha - w * w, (2.0 * alpha + 1.0) * w);
+    const cd aug = cdiv(phi, den);
+    const cd ph = cis(b * j * ada);  // evaluated on the rounded product, like the reference
+    const double wt = j == 0 ? 1.0 : ((j & 1) ? 4.0 : 2.0);
+    const cd v = aug * ph;
+    const double sc = discount * wt;
+    return mk(v.x * sc, v.y * sc);
+  }
+};
+struct CmEpi {
+  double* out;
+  int N;
+  double S0, alpha, b, lambda, ada, discount;
+  int is_put;
+  // call_m = S0 Re(X_m) e^{-alpha(-b + lambda m)} ada/(3 pi)  (:605);  put by parity (:652)
+  __device__ void operator()(int p, int k, cd X) const {
+    const double kk = -b + lambda * k;
+    double v = S0 * X.x * exp(-alpha * kk) * ada / (M_PI * 3.0);
+    if (is_put) v = v - S0 + S0 * exp(kk) * discount;
+    out[(size_t)p * N + k] = v;
+  }
+};
+
+// runs `batch` transforms of length N through the engine
+template <int SIGN, typename Gen, typename Epi>
+int run_fft(fop_handle_t h, Arena& ar, int N, int batch, Gen gen, Epi epi) {
+  const int n = ilog2(N);
+  if (n <= 13) {
+    const double2* tw = nullptr;
+    FOP_TRY(get_twiddles(h, N, &tw));
+    const size_t smem = fft_single_smem(n) + Gen::aux_bytes;
+    auto kern = fft_single_kernel<SIGN, Gen, Epi>;
+    FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tpb = fft_single_tpb(n);
+    const int groups = (batch + tpb - 1) / tpb;
+    const int grid = std::min(groups, h->sm_count * 8);
+    kern<<<grid, fft_single_threads(n), smem, h->stream>>>(n, batch, tw, gen, epi);
+    FOP_LAUNCH_CHECK(h);
+    return FOP_OK;
+  }
+  const FourStep f = four_step_plan(n);
+  const int N1 = 1 << f.n1, N2 = 1 << f.n2;
+  const double2 *tw1 = nullptr, *tw2 = nullptr, *twN = nullptr;
+  FOP_TRY(get_twiddles(h, N1, &tw1));
+  FOP_TRY(get_twiddles(h, N2, &tw2));
+  FOP_TRY(get_twiddles(h, N, &twN));
+  // scratch for up to `pb` transforms in flight (<= 512 MiB)
+  const int pb = (int)std::max<long long>(1, std::min<long long>(batch, (512ll << 20) / ((long long)N * 16)));
+  cd* scratch = ar.alloc<cd>((size_t)pb * N);
+  if (!scratch) return fail(h, FOP_OOM, "arena exhausted for four-step scratch");
+  auto ka = fft_cols_kernel<SIGN, Gen>;
+  auto kb = fft_rows_kernel<SIGN, Epi>;
+  const size_t sa = four_step_smem(f.n1, f.ta) + Gen::aux_bytes, sb = four_step_smem(f.n2, f.tb);
+  FOP_CUDA(h, cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa));
+  FOP_CUDA(h, cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
+  for (int p0 = 0; p0 < batch; p0 += pb) {
+    const int pc = std::min(pb, batch - p0);
+    ka<<<dim3(N2 / f.ta, pc), f.ta * (N1 / 16), sa, h->stream>>>(f, p0, tw1, twN, gen, scratch);
+    FOP_LAUNCH_CHECK(h);
+    kb<<<dim3(N1 / f.tb, pc), f.tb * (N2 / 16), sb, h->stream>>>(f, p0, tw2, scratch, epi);
+    FOP_LAUNCH_CHECK(h);
+  }
+  return FOP_OK;
+}
+size_t fft_scratch_bytes(int N, int batch) {
+  if (ilog2(N) <= 13) return 0;
+  const long long pb = std::max<long long>(1, std::min<long long>(batch, (512ll << 20) / ((long long)N * 16)));
+  return Arena::pad((size_t)pb * N * 16);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fop_fft(fop_handle_t h, double* data, int batch, int N, int inverse) {
+  if (!h) return FOP_INVALID_ARG;
+  if (!data || batch < 0 || N < 2 || (N & (N - 1)) || N > (1 << 20))
+    return fail(h, FOP_INVALID_ARG, "fop_fft: need data, batch >= 0, N a power of two in [2, 2^20]");
+  if (batch == 0) return FOP_OK;
+  FOP_CUDA(h, cudaSetDevice(h->device));
+  const bool host = !is_device_ptr(data);
+  const size_t bytes = (size_t)batch * N * 16;
+  Arena ar(h);
+  FOP_TRY(ar.reserve((host ? Arena::pad(bytes) : 0) + fft_scratch_bytes(N, batch)));
+  cd* d = reinterpret_cast<cd*>(data);
+  if (host) {
+    d = ar.alloc<cd>((size_t)batch * N);
+    FOP_CUDA(h, cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (N < 16) {
+    tiny_dft_kernel<<<(batch + 127) / 128, 128, 0, h->stream>>>(d, batch, N, inverse ? 1 : -1);
+    FOP_LAUNCH_CHECK(h);
+  } else {
+    LoadGen g{d, N};
+    StoreEpi e{d, N};
+    if (inverse) FOP_TRY((run_fft<1>(h, ar, N, batch, g, e)));
+    else FOP_TRY((run_fft<-1>(h, ar, N, batch, g, e)));
+  }
+  if (host) {
+    FOP_CUDA(h, cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, h->stream));
+    FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return FOP_OK;
+}
+
+int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int P, int N,
+                   double ada, double alpha, double S0, double r, double T, int is_put,
+                   double* out) {
+  if (!h) return FOP_INVALID_ARG;
+  const int np = num_params(model.base, model.time_change);
+  if (np == 0) return fail(h, FOP_INVALID_ARG, "unknown model (%d,%d)", model.base, model.time_change);
+  if (!params || !out) return fail(h, FOP_INVALID_ARG, "null pointer");
+  if (P < 0 || N < 16 || (N & (N - 1)) || N > (1 << 20))
+    return fail(h, FOP_INVALID_ARG, "fop_carr_madan: N must be a power of two in [16, 2^20]");
+  if (P == 0) return FOP_OK;
+  FOP_CUDA(h, cudaSetDevice(h->device));
+  const bool out_host = !is_device_ptr(out);
+  // host-bound outputs are produced in chunks of <= 1 GiB of device staging
+  const long long chunkP = out_host ? std::max<long long>(1, std::min<long long>(P, (1ll << 30) / ((long long)N * 8))) : P;
+  Arena ar(h);
+  FOP_TRY(ar.reserve(stage_bytes(params, (size_t)P * np * 8) +
+                     (out_host ? Arena::pad((size_t)chunkP * N * 8) : 0) +
+                     fft_scratch_bytes(N, (int)chunkP)));
+  const double* d_params = nullptr;
+  FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
+  double* d_tmp = out_host ? ar.alloc<double>((size_t)chunkP * N) : nullptr;
+  const double b = M_PI / ada;        // getMaxK,  OptionPricing.h:31-33
+  const double lambda = 2.0 * b / N;  // getLambda, :40-42
+  const double discount = std::exp(-r * T);
+  const size_t scratch_mark = h->arena_used;
+  for (long long p0 = 0; p0 < P; p0 += chunkP) {
+    const int pc = (int)std::min<long long>(chunkP, P - p0);
+    h->arena_used = scratch_mark;  // four-step scratch is re-used by every chunk
+    CmGen g{model.base, model.time_change, np, d_params + (size_t)p0 * np, r, T, ada, alpha, discount, b};
+    CmEpi e{out_host ? d_tmp : out + (size_t)p0 * N, N, S0, alpha, b, lambda, ada, discount, is_put};
+    FOP_TRY((run_fft<-1>(h, ar, N, pc, g, e)));
+    if (out_host)
+      FOP_CUDA(h, cudaMemcpyAsync(out + (size_t)p0 * N, d_tmp, (size_t)pc * N * 8,
+                                  cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (out_host) FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FOP_OK;
+}
+
+}  // extern "C"

@@ -45,9 +45,16 @@ __device__ __forceinline__ cd cis(double t) {
   sincos(t, &s, &c);
   return mk(c, s);
 }
-// principal log: Im in (-pi, pi]
+// principal log: Im in (-pi, pi].  |z| is formed after scaling by a power of two so that tiny or
+// huge CF values (FSTS theta takes log of phi ~ 1e-200) neither underflow nor overflow, matching
+// libstdc++'s log(hypot(x, y)).
 __device__ __forceinline__ cd clog(cd z) {
-  return mk(0.5 * log(z.x * z.x + z.y * z.y), atan2(z.y, z.x));
+  const double big = fmax(fabs(z.x), fabs(z.y));
+  int e = ((__double2hiint(big) >> 20) & 0x7ff) - 1023;
+  e = max(-1020, min(1020, e));
+  const double sc = __hiloint2double((1023 - e) << 20, 0);  // 2^-e, exact
+  const double xs = z.x * sc, ys = z.y * sc;
+  return mk(fma((double)e, 0.69314718055994530942, 0.5 * log(xs * xs + ys * ys)), atan2(z.y, z.x));
 }
 // principal square root (Re >= 0; on the negative real axis the sign of Im follows the sign of z.y)
 __device__ __forceinline__ cd csqrt(cd z) {

@@ -198,12 +198,10 @@ FOP_HD int fft_base16(int b, int S) { return (b / S) * (S << 4) + (b % S); }
 template <int SIGN>
 FOP_HD void dif16_regs(cd* x, int q, int twstride, const double2* __restrict__ tw) {
   Dft<16, SIGN>::run(x);
-  if (q != 0 || true) {
 #pragma unroll
-    for (int k = 1; k < 16; ++k) {
-      const int r = Dft<16, SIGN>::out(k);
-      x[r] = x[r] * tw_load<SIGN>(tw, q * k * twstride);
-    }
+  for (int k = 1; k < 16; ++k) {
+    const int r = Dft<16, SIGN>::out(k);
+    x[r] = x[r] * tw_load<SIGN>(tw, q * k * twstride);
   }
 }
 // DIT: input twiddles then butterfly
@@ -275,61 +273,67 @@ FOP_HD void unpermute16(cd* x) {
 }
 
 // ---------------------------------------------------------------- whole transforms
-// `sync` is a functor (e.g. [] { __syncthreads(); }); every thread of the group calls it the same
-// number of times.  b in [0, N/16), N = 2^n >= 16.
-//
-// Forward/inverse DIF over data already in shared memory (natural order) -> digit-reversed in
-// shared memory.
-template <int SIGN, typename Sync>
-FOP_HD void fft_dif_smem(cd* sm, int b, int n, const double2* __restrict__ tw, Sync sync) {
+// One pass for one thread; b in [0, N/16), N = 2^n >= 16, p in [0, fft_num_passes(n)).
+// DIF: natural-order input -> digit-reversed output (passes run p = 0, 1, ...).
+template <int SIGN>
+FOP_HD void fft_dif_pass(cd* sm, int b, int n, int p, const double2* __restrict__ tw) {
   const int N = 1 << n;
-  const int np = fft_num_passes(n);
   const int rl = fft_last_radix(n);
+  const int n16 = fft_num_passes(n) - (rl == 16 ? 0 : 1);  // number of radix-16 passes
   cd x[16];
-  int S = N >> 4;
-  for (int p = 0; p < np - (rl == 16 ? 0 : 1); ++p) {
+  if (p < n16) {
+    const int S = N >> (4 * (p + 1));
     const int base = fft_base16(b, S), q = b % S;
     load16(sm, base, S, x);
-    dif16_regs<SIGN>(x, q, (N / (S << 4)), tw);
+    dif16_regs<SIGN>(x, q, N / (S << 4), tw);
     store16_dft<SIGN>(sm, base, S, x);
-    sync();
-    S >>= 4;
-  }
-  if (rl != 16) {
+  } else {
     load16(sm, 16 * b, 1, x);
     if (rl == 8) last_pass_regs<8, SIGN>(x);
     else if (rl == 4) last_pass_regs<4, SIGN>(x);
     else last_pass_regs<2, SIGN>(x);
     store16(sm, 16 * b, 1, x);
+  }
+}
+// DIT: digit-reversed input -> natural-order output; the exact transpose of the DIF passes, run
+// in the opposite order (small last radix first, then strides rl, 16 rl, ...).
+template <int SIGN>
+FOP_HD void fft_dit_pass(cd* sm, int b, int n, int p, const double2* __restrict__ tw) {
+  const int N = 1 << n;
+  const int rl = fft_last_radix(n);
+  cd x[16];
+  if (rl != 16 && p == 0) {
+    load16(sm, 16 * b, 1, x);
+    if (rl == 8) last_pass_regs<8, SIGN>(x);
+    else if (rl == 4) last_pass_regs<4, SIGN>(x);
+    else last_pass_regs<2, SIGN>(x);
+    store16(sm, 16 * b, 1, x);
+    return;
+  }
+  const int p16 = rl == 16 ? p : p - 1;  // index among the radix-16 passes
+  const int S = (rl == 16 ? 1 : rl) << (4 * p16);
+  const int base = fft_base16(b, S), q = b % S;
+  load16(sm, base, S, x);
+  dit16_regs<SIGN>(x, q, N / (S << 4), tw);
+  store16_dft<SIGN>(sm, base, S, x);
+}
+
+// `sync` is a functor (e.g. [] { __syncthreads(); }); every thread of the group calls it the same
+// number of times (once after every pass).
+template <int SIGN, typename Sync>
+FOP_HD void fft_dif_smem(cd* sm, int b, int n, const double2* __restrict__ tw, Sync sync) {
+  const int np = fft_num_passes(n);
+  for (int p = 0; p < np; ++p) {
+    fft_dif_pass<SIGN>(sm, b, n, p, tw);
     sync();
   }
 }
-// The radix-16 passes before a small last pass need twiddles W_L^{q k} with L = 16 S where S is
-// a multiple of the last radix; nothing else changes, so the loop above covers all plans.
-//
-// DIT: digit-reversed input in shared memory -> natural order in shared memory.
 template <int SIGN, typename Sync>
 FOP_HD void fft_dit_smem(cd* sm, int b, int n, const double2* __restrict__ tw, Sync sync) {
-  const int N = 1 << n;
   const int np = fft_num_passes(n);
-  const int rl = fft_last_radix(n);
-  cd x[16];
-  if (rl != 16) {
-    load16(sm, 16 * b, 1, x);
-    if (rl == 8) last_pass_regs<8, SIGN>(x);
-    else if (rl == 4) last_pass_regs<4, SIGN>(x);
-    else last_pass_regs<2, SIGN>(x);
-    store16(sm, 16 * b, 1, x);
+  for (int p = 0; p < np; ++p) {
+    fft_dit_pass<SIGN>(sm, b, n, p, tw);
     sync();
-  }
-  int S = rl == 16 ? 1 : rl;
-  for (int p = 0; p < np - (rl == 16 ? 0 : 1); ++p) {
-    const int base = fft_base16(b, S), q = b % S;
-    load16(sm, base, S, x);
-    dit16_regs<SIGN>(x, q, (N / (S << 4)), tw);
-    store16_dft<SIGN>(sm, base, S, x);
-    sync();
-    S <<= 4;
   }
 }
 

@@ -108,7 +108,7 @@ int fop_strike_underlying(double xMin, double xMax, double K, int numX, double* 
 /* ---- Carr-Madan ------------------------------------------------------------------------------
  * Replaces optionprice::CarrMadanCall / CarrMadanPut (OptionPricing.h:620-656, :670-704; pass
  * alpha = 1.5 for the 6-argument overloads) and CarrMadanGeneric (:582-607), batched over P
- * parameter sets.  N must be a power of two, 2 <= N <= 2^20.
+ * parameter sets.  N must be a power of two, 16 <= N <= 2^20.
  *   params [P][np]   out [P][N]   (index i <-> strike fop_carr_madan_strikes()[i])
  */
 int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int P, int N,
@@ -133,7 +133,7 @@ int fop_cos(fop_handle_t h, fop_model_t model, const double* params, int P,
  * steps > 1 applies the one-step operator with dt = T/steps repeatedly; american != 0 takes
  * max(value, payoff) after every step (README.md:19 -- not implemented by the reference; defined
  * in SURVEY.md A.4).  steps > 1 needs a Levy model (FOP_TC_NONE) and kind FOP_FSTS_PRICE.
- * N power of two, 4 <= N <= 8192.   out [P][N]  (node j <-> asset fop_strike_underlying(-xmax,
+ * N power of two, 16 <= N <= 4096.  out [P][N]  (node j <-> asset fop_strike_underlying(-xmax,
  * xmax, strike, N)[j])
  */
 int fop_fsts(fop_handle_t h, fop_model_t model, const double* params, int P, int N, double xmax,

@@ -36,21 +36,21 @@ for P in (16384, 131072):
     prm = torch.tensor(CASES.heston_batch(P), device=dev)
     K = CASES.c5_strikes()
     out = torch.empty((P, 8, 66), dtype=torch.float64, device=dev)
-    for var in (None, "2,2"):
-        if var: os.environ["FOP_COS_VARIANT"] = var
-        else: os.environ.pop("FOP_COS_VARIANT", None)
+    for var in (None, "fused"):
+        if var: os.environ["FOP_COS_FUSED"] = "1"
+        else: os.environ.pop("FOP_COS_FUSED", None)
         best, med = time_call(lambda: eng.cos(0, 1, prm, K, 100.0, 0.0, CASES.C5_T, 256, 0, out=out))
         res[f"c5 P={P} variant={var}"] = dict(ms=best, ms_med=med, prices_per_s=P * 8 * 64 / (best * 1e-3))
         print(res, flush=True)
-os.environ.pop("FOP_COS_VARIANT", None)
+os.environ.pop("FOP_COS_FUSED", None)
 # C2: P sets x 1024 strikes
-for P in (4096,):
+for P in (4096, 65536):
     prm = torch.tensor(CASES.heston_batch(P), device=dev)
     K = CASES.fang_oost_strikes(-5.0, 5.0, 100.0, 1024)
     out = torch.empty((P, 1, 1024), dtype=torch.float64, device=dev)
-    for var in (None, "2,2"):
-        if var: os.environ["FOP_COS_VARIANT"] = var
-        else: os.environ.pop("FOP_COS_VARIANT", None)
+    for var in (None, "fused"):
+        if var: os.environ["FOP_COS_FUSED"] = "1"
+        else: os.environ.pop("FOP_COS_FUSED", None)
         best, med = time_call(lambda: eng.cos(0, 1, prm, K, 100.0, 0.0, [1.0], 256, 0, out=out))
         res[f"c2 P={P} variant={var}"] = dict(ms=best, ms_med=med, prices_per_s=P * 1024 / (best * 1e-3),
                                              tflops=P * 1024 * 1024 / (best * 1e-3) / 1e12)
