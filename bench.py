@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 Fourier option-pricing hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[4], the configuration the metric / north-star target is quoted
+on): Heston (CIR-time-changed Brownian motion, generateCharts.cpp:231-250) COS calibration sweep,
+8 maturities x 66 strikes (64 quoted + the two synthetic far strikes of generateCharts.cpp:43-48),
+numU = 256, weak scaling with 125 000 parameter sets per GPU (8 GPUs = the 1e6-set sweep).
+One step = one pass over the rank's shard: every strike price is computed, written to HBM,
+reduced to the per-set weighted squared error against market quotes (fop_cos_loss), and for N > 1
+the per-set losses are all-gathered over NCCL.  A price counts once per (set, maturity, quoted
+strike): 64 per row, although 66 are evaluated.
+
+Prints ONE JSON line (rank 0).  `value` = prices/s with inputs resident in HBM; `e2e` = the same
+through the C ABI with HOST buffers (H2D of the parameter sets and D2H of the losses inside the
+timed region); `roofline` = live CUDA-event timing of the dominant kernel against the fp64 peak
+measured in the same process; `cpu_baseline` = the reference's own headers (oracle/_ref) on the
+host cores over a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests import cases as CASES  # noqa: E402  (synthetic inputs of SURVEY.md 8d; no oracle code)
+
+METRIC = "option prices/sec (fp64, batched param sets x strikes)"
+UNIT = "prices/s"
+SETS_PER_GPU = 125_000
+NUM_U = 256
+S0, RATE = 100.0, 0.0
+COUNTED_STRIKES = 64
+
+
+def workload_config(sets_per_gpu, n_gpus):
+    return {
+        "workload": "C5 Heston COS calibration sweep (BASELINE.json configs[4]): "
+                    f"{sets_per_gpu} parameter sets/GPU x 8 maturities x 64 quoted strikes "
+                    "(+2 synthetic end strikes evaluated), numU=256, fused per-set loss, "
+                    "NCCL all-gather of losses for N>1",
+        "sets_per_gpu": sets_per_gpu,
+        "global_sets": sets_per_gpu * n_gpus,
+        "maturities": len(CASES.C5_T),
+        "strikes_counted": COUNTED_STRIKES,
+        "strikes_evaluated": 66,
+        "numU": NUM_U,
+        "model": "GAUSS+CIR time change (the reference's Heston)",
+        "parallelism": f"parameter sets sharded over {n_gpus} GPU(s), no data-path collective; "
+                       "loss all-gather only",
+        "l2_policy": "working set per step (1 GiB coefficient matrix + 528 MB prices) >> 126 MB L2",
+    }
+
+
+def market_and_weights(K, T):
+    # synthetic "market": Black-Scholes prices at a fixed vol (inputs only; identical bytes for
+    # every arm).  End strikes carry weight 0.
+    import math
+    mkt = np.array([[CASES.bs_call(S0, math.exp(-RATE * t), k, 0.25, t) for k in K] for t in T])
+    return mkt, CASES.c5_weights()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def load_ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary (or None)."""
+    path = os.path.join(ROOT, "profiles", "r1_cos_c5_ncu.json")
+    try:
+        for k in json.load(open(path)):
+            if "cos_gemm_kernel" in k["kernel"]:
+                def mb(s):
+                    v, u = s.split()[:2]
+                    return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+                return {"bytes": mb(k["dram__bytes_read.sum"]) + mb(k["dram__bytes_write.sum"]),
+                        "rows": k.get("rows")}
+    except Exception:
+        pass
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(seconds_target, sets_hint=None):
+    """Times the reference CPU implementation (oracle/_ref = reference headers + shims, else the
+    port) on a bounded sample of the workload.  The only place bench.py touches oracle/."""
+    from oracle import build as obuild
+    from oracle import oracle as O
+    obuild.build()
+    ora = O.load("best")
+    K, T = CASES.c5_strikes(S0), CASES.C5_T
+    mkt, w = market_and_weights(K, T)
+    nthreads = ora.num_threads
+    probe = max(8, 2 * nthreads)
+    prm = CASES.heston_batch(probe)
+    t0 = time.perf_counter()
+    ora.cos_loss(0, 1, prm, K, S0, RATE, T, NUM_U, mkt, w)
+    dt = time.perf_counter() - t0
+    nsets = sets_hint or int(max(probe, min(200_000, probe * seconds_target / max(dt, 1e-6))))
+    prm = CASES.heston_batch(nsets)
+    t0 = time.perf_counter()
+    ora.cos_loss(0, 1, prm, K, S0, RATE, T, NUM_U, mkt, w)
+    dt = time.perf_counter() - t0
+    rate = nsets * len(T) * COUNTED_STRIKES / dt
+    return {"value": rate, "unit": UNIT, "cores": nthreads,
+            "kind": "reference" if ora.flavor == "reference" else "port",
+            "sample": f"{nsets} parameter sets x 8 maturities x 66 strikes of the same workload "
+                      f"(FangOostCallPrice + loss per set, OpenMP over sets, {dt:.1f} s)",
+            "seconds": dt, "sets": nsets}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warm = args.steps, args.warmup
+    first = cpu_reference_rate(seconds_target=2.0)
+    # size each step for ~2 s so the whole run stays within a few minutes
+    sets = max(16, int(first["sets"] * 2.0 / max(first["seconds"], 1e-6)))
+    sets = min(sets, 50_000)
+    for _ in range(warm):
+        cpu_reference_rate(0, sets_hint=sets)
+    t0 = time.perf_counter()
+    res = None
+    for _ in range(steps):
+        res = cpu_reference_rate(0, sets_hint=sets)
+    dt = time.perf_counter() - t0
+    value = steps * sets * len(CASES.C5_T) * COUNTED_STRIKES / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(SETS_PER_GPU, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
+                         "sample": f"each step = {sets} parameter sets x 8 maturities x 66 strikes "
+                                   "of the workload on the host cores (reference headers compiled "
+                                   "against oracle/shims, OpenMP over sets)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import fftoptionpricing_b200 as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    eng = F.Engine(local)
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
+
+    P = args.sets_per_gpu
+    K, T = CASES.c5_strikes(S0), CASES.C5_T
+    M, J = len(T), len(K)
+    mkt, w = market_and_weights(K, T)
+    # rank r prices the r-th contiguous slice of the global sweep (seeded synthetic inputs)
+    prm_host = torch.from_numpy(CASES.heston_batch(P, seed=CASES.SEED + 1000 * rank)).pin_memory()
+    loss_host = torch.empty(P, dtype=torch.float64).pin_memory()
+    prm_dev = prm_host.to(dev)
+    prices = torch.empty((P, M, J), dtype=torch.float64, device=dev)
+    loss = torch.empty(P, dtype=torch.float64, device=dev)
+    gathered = torch.empty(P * world, dtype=torch.float64, device=dev) if world > 1 else None
+    mkt_d = torch.from_numpy(mkt).to(dev)
+    w_d = torch.from_numpy(w).to(dev)
+
+    def step_device():
+        eng.cos_loss(F.GAUSS, F.TC_CIR, prm_dev, K, S0, RATE, T, NUM_U, mkt_d, w_d, out=loss,
+                     prices_out=prices)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, loss)
+
+    def step_host():
+        # host buffers in, host losses out: H2D of the parameter sets + D2H of the losses happen
+        # inside the call (which returns after the stream is idle)
+        # inside the call (which returns after the stream is idle); prices are stored to HBM exactly
+        # as in the device-resident step
+        eng.cos_loss(F.GAUSS, F.TC_CIR, prm_host.numpy(), K, S0, RATE, T, NUM_U, mkt, w,
+                     out=loss_host.numpy(), prices_out=prices)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+        barrier()
+        # ---- timed region: device-resident inputs
+        sampler = ClockSampler(local) if rank == 0 else None
+        l0 = eng.launch_count
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = eng.launch_count - l0
+        clocks = sampler.stop() if sampler else None
+
+        # ---- end to end through the C ABI with host buffers
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, loss_host.to(dev, non_blocking=True))
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+        # ---- per-kernel timing for the roofline (separate pass so events do not perturb `value`)
+        eng.profile_enable(True)
+        for _ in range(args.steps):
+            eng.cos_loss(F.GAUSS, F.TC_CIR, prm_dev, K, S0, RATE, T, NUM_U, mkt_d, w_d, out=loss,
+                         prices_out=prices)
+        prof = eng.profile_read()
+        eng.profile_enable(False)
+        peaks = eng.microbench_fp64() if rank == 0 else None
+
+    # max over ranks
+    t = torch.tensor([ms, e2e_s * 1e3, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, e2e_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+    else:
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        prices_per_step = world * P * M * COUNTED_STRIKES
+        value = prices_per_step * args.steps / (ms * 1e-3)
+        e2e_value = prices_per_step * args.steps / (e2e_ms * 1e-3)
+        rows = P * M
+        gemm_ms, gemm_n = prof.get("cos_gemm_kernel", (0.0, 0))
+        coef_ms, coef_n = prof.get("cos_coeff_kernel", (0.0, 0))
+        peak = max(peaks[0], peaks[1])
+        # algorithmic flops of the contraction: 4*numU per evaluated price
+        gemm_flops_per_launch = rows * J * 4.0 * NUM_U / max(gemm_n / args.steps, 1)
+        gemm_avg_s = gemm_ms * 1e-3 / max(gemm_n, 1)
+        achieved = gemm_flops_per_launch / gemm_avg_s / 1e12 if gemm_n else None
+        traffic = load_ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(P, world),
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(prm_host.numel() * 8 + (J + M + 2 * M * J) * 8),
+                    "d2h_bytes_per_step": int(P * 8), "ms_per_step": e2e_ms / args.steps,
+                    "what": "fop_cos_loss with host parameter sets in / host losses out"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "fp64", "kernel": "cos_gemm_kernel", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                "traffic": traffic["bytes"] if traffic else None,
+                "peak_source": "fp64 FMA/DMMA throughput measured live in this process "
+                               "(fop_microbench_fp64: DFMA %.1f, DMMA m8n8k4 %.1f TFLOP/s); "
+                               "MEASURED_PEAKS.json has no fp64 entry" % (peaks[0], peaks[1]),
+                "algorithmic_flops_per_launch": gemm_flops_per_launch,
+                "avg_launch_ms": gemm_avg_s * 1e3,
+                "share_of_step": gemm_ms / max(gemm_ms + coef_ms, 1e-9),
+            },
+            "kernels": {
+                k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                for k, v in prof.items()},
+            "cf_evals_per_s": (P * M * NUM_U * args.steps / (coef_ms * 1e-3)) if coef_n else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(args.cpu_seconds).items()
+                                    if k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--sets-per-gpu", type=int, default=SETS_PER_GPU)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

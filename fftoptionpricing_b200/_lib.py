@@ -30,6 +30,9 @@ _SIGNATURES = {
     "fop_get_stream": (C.c_void_p, [C.c_void_p]),
     "fop_synchronize": (C.c_int, [C.c_void_p]),
     "fop_launch_count": (C.c_longlong, [C.c_void_p]),
+    "fop_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "fop_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, _dp, C.POINTER(C.c_longlong),
+                                   C.c_int, C.POINTER(C.c_int)]),
     "fop_model_num_params": (C.c_int, [fop_model_t]),
     "fop_carr_madan_strikes": (C.c_int, [C.c_int, C.c_double, C.c_double, _dp]),
     "fop_fang_oost_strikes": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_int, _dp]),

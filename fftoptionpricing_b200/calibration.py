@@ -1,0 +1,63 @@
+"""Mirror of namespace ``optioncal``'s hot function (reference OptionCalibration.h:185-201) and the
+price-space sweep of BASELINE.json config 5, plus the multi-GPU sharding of parameter sets.
+
+Parameter sets are independent, so N ranks each price a contiguous slice and the only exchange
+is an all-gather of the per-set losses (torch.distributed: NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import engine as E
+from .models import CF
+
+largeNumber = 5000.0  # OptionCalibration.h:185
+
+
+def getObjFn_arr(phiHat, model: CF, uArray, r: float, T: float, engine: Optional[E.Engine] = None):
+    """Returns ``objFn(params)``: for a batch of parameter vectors [P][np] the vector of
+    mean_l |phiHat_l - logCF_theta(1 + i u_l)|^2 with NaN -> 5000 (OptionCalibration.h:186-201).
+    `model.params` is ignored (only the model family is used)."""
+    phiHat = np.ascontiguousarray(np.asarray(phiHat, dtype=np.complex128))
+    uArray = np.ascontiguousarray(np.asarray(uArray, dtype=np.float64))
+
+    def objFn(params):
+        from .pricing import default_engine
+        eng = engine or default_engine()
+        return eng.objfn_cf(model.base, model.time_change, params, uArray, phiHat, r, T)
+
+    return objFn
+
+
+def shard_bounds(total: int, rank: int, world: int):
+    """Contiguous [lo, hi) slice of `total` parameter sets owned by `rank` (sizes differ by <= 1)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def sharded_losses(params: np.ndarray, compute: Callable[[np.ndarray], "np.ndarray"],
+                   device=None):
+    """Evaluates `compute` (e.g. a bound Engine.cos_loss) on this rank's slice of `params` and
+    all-gathers the per-set losses; every rank returns the full [P] vector in set order.
+    Works with any initialised torch.distributed backend; without one it is a plain call."""
+    import torch
+    import torch.distributed as dist
+    P = params.shape[0]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return np.asarray(compute(params))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lo, hi = shard_bounds(P, rank, world)
+    local = compute(params[lo:hi])
+    cap = -(-P // world)  # all_gather needs equal sizes: pad to the largest shard
+    dev = device or ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    buf = torch.zeros(cap, dtype=torch.float64, device=dev)
+    buf[: hi - lo] = torch.as_tensor(np.asarray(local), dtype=torch.float64, device=dev)
+    out = torch.empty(cap * world, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, buf) if dev != "cpu" else dist.all_gather(
+        list(out.view(world, cap).unbind(0)), buf)
+    out = out.view(world, cap).cpu().numpy()
+    return np.concatenate([out[r, : shard_bounds(P, r, world)[1] - shard_bounds(P, r, world)[0]]
+                           for r in range(world)])

@@ -144,7 +144,10 @@ int fop_destroy(fop_handle_t h) {
     cudaStreamDestroy(h->stream);
   }
   if (h->arena) cudaFree(h->arena);
+  if (h->cos_cache.dev) cudaFree(h->cos_cache.dev);
   for (auto& t : h->twiddles) cudaFree(t.d);
+  for (auto& p : h->prof_pending) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+  for (auto& e : h->event_pool) cudaEventDestroy(e);
   delete h;
   return FOP_OK;
 }
@@ -152,6 +155,45 @@ int fop_destroy(fop_handle_t h) {
 const char* fop_last_error(fop_handle_t h) { return h ? h->err.c_str() : "null handle"; }
 void* fop_get_stream(fop_handle_t h) { return h ? (void*)h->stream : nullptr; }
 long long fop_launch_count(fop_handle_t h) { return h ? h->launches : 0; }
+
+// ---- per-kernel device timing (used by bench.py for the live roofline) ------------------------
+int fop_profile_enable(fop_handle_t h, int enable) {
+  if (!h) return FOP_INVALID_ARG;
+  h->profiling = enable != 0;
+  return FOP_OK;
+}
+// Drains pending events (synchronises the stream), then reports accumulated milliseconds and
+// launch counts per kernel name; names are written NUL-separated into names_buf.  Resets.
+int fop_profile_read(fop_handle_t h, char* names_buf, int buf_len, double* ms_out,
+                     long long* launches_out, int max_entries, int* n_out) {
+  if (!h || !n_out) return FOP_INVALID_ARG;
+  FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (auto& p : h->prof_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+      h->prof[p.entry].ms += ms;
+      h->prof[p.entry].launches += 1;
+    }
+    h->event_pool.push_back(p.e0);
+    h->event_pool.push_back(p.e1);
+  }
+  h->prof_pending.clear();
+  int n = 0, off = 0;
+  for (auto& e : h->prof) {
+    if (n >= max_entries) break;
+    const int len = (int)e.name.size() + 1;
+    if (names_buf && off + len <= buf_len) {
+      memcpy(names_buf + off, e.name.c_str(), len);
+      off += len;
+    }
+    if (ms_out) ms_out[n] = e.ms;
+    if (launches_out) launches_out[n] = e.launches;
+    ++n;
+  }
+  *n_out = n;
+  h->prof.clear();
+  return FOP_OK;
+}
 
 int fop_synchronize(fop_handle_t h) {
   if (!h) return FOP_INVALID_ARG;

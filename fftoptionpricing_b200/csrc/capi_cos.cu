@@ -113,21 +113,53 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   }
   const int JB = 4 * TJ, Jp = nblk * JB, KK = 2 * numU;
 
-  // small host-side tables (strike list may live on the device)
+  // Strike-grid tables (u_k, V_k, strikes, maturities, cos/sin basis): rebuilt only when
+  // (K_desc, S0, T, numU) change -- a calibration loop keeps them fixed while theta varies.
   std::vector<double> Kh(J), Th(M);
   FOP_CUDA(h, cudaMemcpy(Kh.data(), K_desc, sizeof(double) * J, cudaMemcpyDefault));
   FOP_CUDA(h, cudaMemcpy(Th.data(), T, sizeof(double) * M, cudaMemcpyDefault));
-  std::vector<double> tab(2 * (size_t)numU + J);
-  double* uk = tab.data();
-  double* vk = uk + numU;
-  double* x = vk + numU;
-  for (int j = 0; j < J; ++j) x[j] = std::log(S0 / Kh[j]);  // getXFromK, OptionPricing.h:110-117
-  const double xMin = x[0], xMax = x[J - 1];
-  const double du = M_PI / (xMax - xMin), cp = 2.0 / (xMax - xMin);
-  for (int k = 0; k < numU; ++k) {
-    uk[k] = du * k;
-    vk[k] = vk_put(xMin, uk[k], k) * cp * (k == 0 ? 0.5 : 1.0);
+  auto& cc = h->cos_cache;
+  const size_t tab_doubles = 2 * (size_t)numU + 2 * (size_t)J + M;
+  const bool hit = cc.dev && cc.S0 == S0 && cc.numU == numU && cc.JB == JB && cc.Jp == Jp &&
+                   cc.K == Kh && cc.T == Th;
+  if (!hit) {
+    std::vector<double> tab(tab_doubles);
+    double* uk = tab.data();
+    double* vk = uk + numU;
+    double* x = vk + numU;
+    for (int j = 0; j < J; ++j) x[j] = std::log(S0 / Kh[j]);  // getXFromK, OptionPricing.h:110-117
+    std::copy(Kh.begin(), Kh.end(), x + J);
+    std::copy(Th.begin(), Th.end(), x + 2 * J);
+    const double xMin = x[0], xMax = x[J - 1];
+    const double du = M_PI / (xMax - xMin), cp = 2.0 / (xMax - xMin);
+    for (int k = 0; k < numU; ++k) {
+      uk[k] = du * k;
+      vk[k] = vk_put(xMin, uk[k], k) * cp * (k == 0 ? 0.5 : 1.0);
+    }
+    const size_t bytes = (tab_doubles + (size_t)KK * Jp) * 8 + 256;
+    FOP_CUDA(h, cudaStreamSynchronize(h->stream));  // earlier launches may still read the old tables
+    if (cc.bytes < bytes) {
+      if (cc.dev) cudaFree(cc.dev);
+      cc.dev = nullptr;
+      cc.bytes = 0;
+      FOP_CUDA(h, cudaMalloc(&cc.dev, bytes));
+      cc.bytes = bytes;
+    }
+    FOP_CUDA(h, cudaMemcpy(cc.dev, tab.data(), tab_doubles * 8, cudaMemcpyHostToDevice));
+    const size_t boff = (tab_doubles + 1) & ~(size_t)1;  // 16-byte aligned basis
+    const int nb = numU * Jp;
+    {
+      ProfScope ps(h, "cos_basis_kernel");
+      cos_basis_kernel<<<(nb + 255) / 256, 256, 0, h->stream>>>(cc.dev, cc.dev + 2 * numU, numU, J,
+                                                               Jp, cc.dev + boff);
+    }
+    FOP_LAUNCH_CHECK(h);
+    cc.K = Kh;  cc.T = Th;  cc.S0 = S0;  cc.numU = numU;  cc.JB = JB;  cc.Jp = Jp;
   }
+  const double* d_tab = cc.dev;
+  const double* d_K = cc.dev + 2 * numU + J;
+  const double* d_T = cc.dev + 2 * numU + 2 * J;
+  const double* d_basis = cc.dev + ((tab_doubles + 1) & ~(size_t)1);
 
   const bool out_host = out && !is_device_ptr(out);
   const bool loss_host = loss && !is_device_ptr(loss);
@@ -140,8 +172,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const int lossblk = fused ? 1 : nblk;
 
   Arena ar(h);
-  size_t need = Arena::pad(tab.size() * 8) + Arena::pad((size_t)J * 8) + Arena::pad((size_t)M * 8) +
-                Arena::pad((size_t)KK * Jp * 8) + stage_bytes(params, (size_t)P * np * 8);
+  size_t need = stage_bytes(params, (size_t)P * np * 8);
   if (mkt) need += stage_bytes(mkt, (size_t)M * J * 8);
   if (w) need += stage_bytes(w, (size_t)M * J * 8);
   if (!fused) need += Arena::pad((size_t)chunk_rows * KK * 8);
@@ -149,13 +180,6 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   if (loss) need += Arena::pad((size_t)P * M * lossblk * 8) + (loss_host ? Arena::pad((size_t)P * 8) : 0);
   FOP_TRY(ar.reserve(need));
 
-  double* d_tab = ar.alloc<double>(tab.size());
-  double* d_K = ar.alloc<double>(J);
-  double* d_T = ar.alloc<double>(M);
-  double* d_basis = ar.alloc<double>((size_t)KK * Jp);
-  FOP_CUDA(h, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, h->stream));
-  FOP_CUDA(h, cudaMemcpyAsync(d_K, Kh.data(), (size_t)J * 8, cudaMemcpyHostToDevice, h->stream));
-  FOP_CUDA(h, cudaMemcpyAsync(d_T, Th.data(), (size_t)M * 8, cudaMemcpyHostToDevice, h->stream));
   const double *d_params = nullptr, *d_mkt = nullptr, *d_w = nullptr;
   FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
   if (mkt) FOP_TRY(stage_in(h, ar, mkt, (size_t)M * J, &d_mkt));
@@ -165,12 +189,6 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M * lossblk) : nullptr;
   double* d_loss = loss ? (loss_host ? ar.alloc<double>(P) : loss) : nullptr;
 
-  {
-    const int n = numU * Jp;
-    cos_basis_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_tab, d_tab + 2 * numU, numU, J, Jp,
-                                                             d_basis);
-    FOP_LAUNCH_CHECK(h);
-  }
   CosSmem L{};
   size_t gemm_smem = 0;
   if (fused) {
@@ -198,7 +216,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       const int R = cos_rows(v->TR, v->WR);
       const long long ntiles = (rows + R - 1) / R;
       const int grid = (int)std::min<long long>(ntiles, h->sm_count);
-      v->kernel<<<grid, 256 * v->WR, L.total, h->stream>>>(a);
+      {
+        ProfScope ps(h, "cos_fused_kernel");
+        v->kernel<<<grid, 256 * v->WR, L.total, h->stream>>>(a);
+      }
       FOP_LAUNCH_CHECK(h);
     } else {
       CosCoeffArgs ca;
@@ -210,8 +231,11 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ca.T = d_T;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = d_C;
       const int ngroups = (pc + ca.spb - 1) / ca.spb;
       const int cgrid = std::min(ngroups, h->sm_count * 32);
-      if (M >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
-      else cos_coeff_kernel<1><<<cgrid, 256, 0, h->stream>>>(ca);
+      {
+        ProfScope ps(h, "cos_coeff_kernel");
+        if (M >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
+        else cos_coeff_kernel<1><<<cgrid, 256, 0, h->stream>>>(ca);
+      }
       FOP_LAUNCH_CHECK(h);
       CosGemmArgs ga;
       ga.kind = kind;  ga.M = M;  ga.J = J;  ga.KK = KK;  ga.Jp = Jp;  ga.nblk = nblk;
@@ -220,7 +244,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ga.out = out_here;  ga.mkt = d_mkt;  ga.w = d_w;
       ga.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
       const dim3 ggrid((unsigned)((rows + GEMM_RT - 1) / GEMM_RT), (unsigned)nblk);
-      gv->kernel<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
+      {
+        ProfScope ps(h, "cos_gemm_kernel");
+        gv->kernel<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
+      }
       FOP_LAUNCH_CHECK(h);
     }
     if (out_host)
@@ -228,7 +255,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
                                   cudaMemcpyDeviceToHost, h->stream));
   }
   if (loss) {
-    cos_loss_finalize2_kernel<<<(P + 255) / 256, 256, 0, h->stream>>>(d_rowloss, P, M, J, lossblk, d_loss);
+    {
+      ProfScope ps(h, "cos_loss_finalize_kernel");
+      cos_loss_finalize2_kernel<<<(P + 255) / 256, 256, 0, h->stream>>>(d_rowloss, P, M, J, lossblk, d_loss);
+    }
     FOP_LAUNCH_CHECK(h);
     if (loss_host)
       FOP_CUDA(h, cudaMemcpyAsync(loss, d_loss, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));

@@ -124,7 +124,10 @@ int run_fft(fop_handle_t h, Arena& ar, int N, int batch, Gen gen, Epi epi) {
     const int tpb = fft_single_tpb(n);
     const int groups = (batch + tpb - 1) / tpb;
     const int grid = std::min(groups, h->sm_count * 8);
-    kern<<<grid, fft_single_threads(n), smem, h->stream>>>(n, batch, tw, gen, epi);
+    {
+      ProfScope ps(h, Gen::aux_bytes ? "carr_madan_single_kernel" : "fft_single_kernel");
+      kern<<<grid, fft_single_threads(n), smem, h->stream>>>(n, batch, tw, gen, epi);
+    }
     FOP_LAUNCH_CHECK(h);
     return FOP_OK;
   }
@@ -145,9 +148,15 @@ int run_fft(fop_handle_t h, Arena& ar, int N, int batch, Gen gen, Epi epi) {
   FOP_CUDA(h, cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
   for (int p0 = 0; p0 < batch; p0 += pb) {
     const int pc = std::min(pb, batch - p0);
-    ka<<<dim3(N2 / f.ta, pc), f.ta * (N1 / 16), sa, h->stream>>>(f, p0, tw1, twN, gen, scratch);
+    {
+      ProfScope ps(h, Gen::aux_bytes ? "carr_madan_cols_kernel" : "fft_cols_kernel");
+      ka<<<dim3(N2 / f.ta, pc), f.ta * (N1 / 16), sa, h->stream>>>(f, p0, tw1, twN, gen, scratch);
+    }
     FOP_LAUNCH_CHECK(h);
-    kb<<<dim3(N1 / f.tb, pc), f.tb * (N2 / 16), sb, h->stream>>>(f, p0, tw2, scratch, epi);
+    {
+      ProfScope ps(h, Gen::aux_bytes ? "carr_madan_rows_kernel" : "fft_rows_kernel");
+      kb<<<dim3(N1 / f.tb, pc), f.tb * (N2 / 16), sb, h->stream>>>(f, p0, tw2, scratch, epi);
+    }
     FOP_LAUNCH_CHECK(h);
   }
   return FOP_OK;

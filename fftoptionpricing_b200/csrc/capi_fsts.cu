@@ -180,7 +180,10 @@ extern "C" int fop_fsts(fop_handle_t h, fop_model_t model, const double* params,
   FOP_CUDA(h, cudaFuncSetAttribute(fsts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int groups = (P + tpb - 1) / tpb;
   const int grid = std::min(groups, h->sm_count * 4);
-  fsts_kernel<<<grid, fft_single_threads(n), smem, h->stream>>>(a, tw);
+  {
+    ProfScope ps(h, "fsts_kernel");
+    fsts_kernel<<<grid, fft_single_threads(n), smem, h->stream>>>(a, tw);
+  }
   FOP_LAUNCH_CHECK(h);
   if (out_host) {
     FOP_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)P * N * 8, cudaMemcpyDeviceToHost, h->stream));

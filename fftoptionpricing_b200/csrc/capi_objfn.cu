@@ -76,7 +76,10 @@ extern "C" int fop_objfn_cf(fop_handle_t h, fop_model_t model, const double* par
   const size_t smem = sizeof(ModelConsts) * OBJ_WARPS + (size_t)OBJ_WARPS * m * 8;
   FOP_CUDA(h, cudaFuncSetAttribute(objfn_cf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min((P + OBJ_WARPS - 1) / OBJ_WARPS, h->sm_count * 8);
-  objfn_cf_kernel<<<grid, 32 * OBJ_WARPS, smem, h->stream>>>(a);
+  {
+    ProfScope ps(h, "objfn_cf_kernel");
+    objfn_cf_kernel<<<grid, 32 * OBJ_WARPS, smem, h->stream>>>(a);
+  }
   FOP_LAUNCH_CHECK(h);
   if (loss_host) {
     FOP_CUDA(h, cudaMemcpyAsync(loss, a.loss, (size_t)P * 8, cudaMemcpyDeviceToHost, h->stream));

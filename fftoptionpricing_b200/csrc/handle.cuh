@@ -22,6 +22,22 @@ struct fop_handle_s {
   // cached twiddle tables: tw[N] holds e^{-2 pi i k/N}, k < N  (see fft_smem.cuh)
   struct Twiddle { int N; double2* d; };
   std::vector<Twiddle> twiddles;
+  // COS strike-grid cache: u_k, V_k, strikes, maturities and the cos/sin basis depend only on
+  // (K_desc, S0, T, numU), which a calibration loop keeps fixed while theta changes
+  struct CosCache {
+    std::vector<double> K, T;
+    double S0 = 0;
+    int numU = 0, Jp = 0, JB = 0;
+    double* dev = nullptr;  // [uk | vk | x | K | T | basis]
+    size_t bytes = 0;
+  } cos_cache;
+  // optional per-kernel device timing (fop_profile_*): accumulated by kernel name
+  bool profiling = false;
+  struct ProfEntry { std::string name; double ms = 0; long long launches = 0; };
+  std::vector<ProfEntry> prof;
+  struct ProfPending { int entry; cudaEvent_t e0, e1; };
+  std::vector<ProfPending> prof_pending;
+  std::vector<cudaEvent_t> event_pool;
 };
 
 namespace fop {
@@ -104,6 +120,39 @@ inline size_t stage_bytes(const void* src, size_t bytes) {
     int st__ = (expr);             \
     if (st__ != FOP_OK) return st__; \
   } while (0)
+
+// Per-kernel timing scope: { ProfScope ps(h, "kernel_name"); kernel<<<...>>>(...); }
+struct ProfScope {
+  fop_handle_t h;
+  int idx = -1;
+  ProfScope(fop_handle_t hh, const char* name) : h(hh) {
+    if (!h->profiling) return;
+    int e = -1;
+    for (size_t i = 0; i < h->prof.size(); ++i)
+      if (h->prof[i].name == name) e = (int)i;
+    if (e < 0) {
+      h->prof.push_back({name, 0.0, 0});
+      e = (int)h->prof.size() - 1;
+    }
+    auto get = [&]() {
+      cudaEvent_t ev;
+      if (!h->event_pool.empty()) {
+        ev = h->event_pool.back();
+        h->event_pool.pop_back();
+      } else {
+        cudaEventCreate(&ev);
+      }
+      return ev;
+    };
+    fop_handle_s::ProfPending p{e, get(), get()};
+    cudaEventRecord(p.e0, h->stream);
+    h->prof_pending.push_back(p);
+    idx = (int)h->prof_pending.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(h->prof_pending[idx].e1, h->stream);
+  }
+};
 
 #define FOP_LAUNCH_CHECK(h)                                                               \
   do {                                                                                    \

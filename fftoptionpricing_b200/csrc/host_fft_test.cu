@@ -20,15 +20,21 @@ static double run(int n, int sign, bool dit) {
     s = s * 1664525u + 1013904223u; double b = (s >> 8) / 16777216.0 - .5;
     x[j] = C(a, b);
   }
-  // reference DFT via long double direct sum (N <= 8192: fine)
+  // reference DFT: direct long double sum with a long double twiddle table
+  std::vector<long double> wc(N), ws(N);
+  for (int e = 0; e < N; ++e) {
+    const long double ang = sign * 2.0L * 3.14159265358979323846264338327950288L * e / N;
+    wc[e] = cosl(ang);
+    ws[e] = sinl(ang);
+  }
   for (int k = 0; k < N; ++k) {
     long double re = 0, im = 0;
+    int e = 0;
     for (int j = 0; j < N; ++j) {
-      const long long e = ((long long)j * k) % N;
-      const long double ang = sign * 2.0L * 3.14159265358979323846264338327950288L * e / N;
-      const long double c = cosl(ang), sn = sinl(ang);
-      re += x[j].real() * c - x[j].imag() * sn;
-      im += x[j].real() * sn + x[j].imag() * c;
+      re += x[j].real() * wc[e] - x[j].imag() * ws[e];
+      im += x[j].real() * ws[e] + x[j].imag() * wc[e];
+      e += k;
+      if (e >= N) e -= N;
     }
     ref[k] = C((double)re, (double)im);
   }

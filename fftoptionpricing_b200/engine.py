@@ -105,6 +105,20 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._L.fop_launch_count(self._h))
 
+    def profile_enable(self, on: bool = True):
+        """Bracket every kernel launch with CUDA events on the handle's stream."""
+        self._check(self._L.fop_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self):
+        """{kernel name: (total ms, launches)} accumulated since the last read; synchronises."""
+        names = C.create_string_buffer(4096)
+        ms = (C.c_double * 64)()
+        ln = (C.c_longlong * 64)()
+        n = C.c_int()
+        self._check(self._L.fop_profile_read(self._h, names, 4096, ms, ln, 64, C.byref(n)))
+        parts = names.raw.split(b"\0")
+        return {parts[i].decode(): (ms[i], int(ln[i])) for i in range(n.value)}
+
     def measure_fp64_peak(self) -> float:
         v = C.c_double()
         self._check(self._L.fop_measure_fp64_peak(self._h, C.byref(v)))

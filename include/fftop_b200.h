@@ -12,8 +12,9 @@
  *
  * Conventions
  *  - Every array argument may be a HOST or a DEVICE pointer (detected with
- *    cudaPointerGetAttributes).  Host inputs are staged through pinned workspace owned by the
- *    handle; host outputs are copied back and the call returns after the stream is idle.  When all
+ *    cudaPointerGetAttributes).  Host inputs are copied with cudaMemcpyAsync on the handle's
+ *    stream into a workspace owned by the handle (pass pinned memory for full PCIe bandwidth);
+ *    host outputs are copied back and the call returns after the stream is idle.  When all
  *    outputs are device pointers the call only enqueues work on the handle's stream
  *    (fop_get_stream) and returns; use fop_synchronize or your own events.
  *  - All arithmetic is IEEE fp64.  No fast-math, exact sincospi twiddles.
@@ -96,6 +97,14 @@ void* fop_get_stream(fop_handle_t handle);       /* the handle's cudaStream_t */
 int fop_synchronize(fop_handle_t handle);
 /* number of this library's kernel launches since fop_create (for bench.py's gpu_launches) */
 long long fop_launch_count(fop_handle_t handle);
+
+/* Optional per-kernel device timing: while enabled every kernel launch of this library is
+ * bracketed by CUDA events on the handle's stream.  fop_profile_read synchronises, writes the
+ * kernel names NUL-separated into names_buf, accumulated milliseconds and launch counts per name,
+ * the number of names into *n_out, and resets the accumulators. */
+int fop_profile_enable(fop_handle_t handle, int enable);
+int fop_profile_read(fop_handle_t handle, char* names_buf, int buf_len, double* ms_out,
+                     long long* launches_out, int max_entries, int* n_out);
 
 /* ---- grid helpers (host, trivial) ------------------------------------------------------------ */
 /* getCarrMadanStrikes            OptionPricing.h:131-138: K_i = S0 exp(-pi/ada + (2 pi/ada/N) i) */

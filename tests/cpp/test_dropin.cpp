@@ -1,0 +1,78 @@
+// The reference's own test cases (test.cpp) re-expressed against the drop-in headers.
+// Built and run by tests/test_cpp_dropin_gpu.py on a GPU box.
+#include <cmath>
+#include <cstdio>
+#include <deque>
+#include <vector>
+
+#include "fftop/OptionCalibration.h"
+#include "fftop/OptionPricing.h"
+
+static int failures = 0;
+// Catch v1 Approx semantics: |a-b| < eps (1 + max(|a|,|b|))
+#define REQUIRE_APPROX(a, b, eps)                                                       \
+  do {                                                                                  \
+    const double a_ = (a), b_ = (b);                                                    \
+    if (!(std::fabs(a_ - b_) < (eps) * (1.0 + std::fmax(std::fabs(a_), std::fabs(b_))))) { \
+      std::printf("FAIL %s:%d  %.12g vs %.12g\n", __FILE__, __LINE__, a_, b_);          \
+      ++failures;                                                                       \
+    }                                                                                   \
+  } while (0)
+
+// test.cpp:13-21
+static double BSCall(double S0, double discount, double k, double sigma, double T) {
+  const double s = std::sqrt(2.0), ss = std::sqrt(T) * sigma;
+  const double d1 = std::log(S0 / (discount * k)) / ss + ss * .5;
+  return S0 * (.5 + .5 * std::erf(d1 / s)) - k * discount * (.5 + .5 * std::erf((d1 - ss) / s));
+}
+
+int main() {
+  const double r = .05, sig = .3, T = 1.0, S0 = 50.0, discount = std::exp(-r * T);
+  {  // CarrMadanCall, test.cpp:619-648
+    const int numX = 1024;
+    const double ada = .25;
+    auto price = optionprice::CarrMadanCall(numX, ada, S0, r, T, fftop::blackScholes(sig));
+    auto K = optionprice::getCarrMadanStrikes(ada, S0, numX);
+    for (int i = (int)(numX * .3); i < (int)(numX * .7); ++i)
+      REQUIRE_APPROX(price[i], BSCall(S0, discount, K[i], sig, T), 1e-4);
+  }
+  {  // FangOosterleeCallFewKLowT with a std::deque, test.cpp:562-588
+    std::deque<double> K = {7500, 60, 50, 40, .3};
+    const double Tl = .25;
+    auto price = optionprice::FangOostCallPrice(S0, K, r, Tl, 256, fftop::blackScholes(sig));
+    for (int i = 1; i < 4; ++i) REQUIRE_APPROX(price[i], BSCall(S0, std::exp(-r * Tl), K[i], sig, Tl), 1e-4);
+  }
+  {  // FSTSCall, test.cpp:47-79
+    const int numX = 1024;
+    const double xmax = 5.0, K = 50.0;
+    auto price = optionprice::FSTSPrice(numX, xmax, r, T, K, fftop::Payoff::Call, fftop::blackScholes(sig));
+    auto S = optionprice::getStrikeUnderlying(-xmax, xmax, K, numX);
+    for (int i = (int)(numX * .3); i < (int)(numX * .7); ++i)
+      REQUIRE_APPROX(price[i], BSCall(S[i], discount, K, sig, T), 1e-4);
+  }
+  {  // FangOosterleePutCGMYWithVol, test.cpp:799-829 (12-digit constant)
+    std::vector<double> K = {7500, 500.0, .3};
+    auto p = optionprice::FangOostPutPrice(500.0, K, .4, .25, 256, fftop::cgmy(.2, 1.0, 1.4, 2.5, 1.4));
+    REQUIRE_APPROX(p[1], 108.445317144, 1e-10);
+  }
+  {  // CarrMadanCGMY, test.cpp:831-865
+    auto p = optionprice::CarrMadanPut(1024, .25, 500.0, .4, .25, fftop::cgmy(.2, 1.0, 1.4, 2.5, 1.4));
+    REQUIRE_APPROX(p[512], 108.4614527579, 1e-10);
+  }
+  {  // FangOostHeston, test.cpp:1033-1068
+    const double b = .0398, a = 1.5768, c = .5751, rho = -.5711, v0 = .0175;
+    std::vector<double> K = {5000, 100, .3};
+    auto p = optionprice::FangOostCallPrice(100.0, K, 0.0, 1.0, 256,
+                                            fftop::heston(std::sqrt(b), a, c / std::sqrt(b), rho, v0 / b));
+    REQUIRE_APPROX(p[1], 5.78515545, 1e-4);
+  }
+  {  // getObjFn_arr: NaN -> 5000 penalty (OptionCalibration.h:185,196) and exactness at the target
+    std::vector<double> u = {6, 7, 8};
+    std::vector<std::complex<double>> ph(3, std::complex<double>(0.0, 0.0));
+    auto hoc = optioncal::getObjFn_arr(std::move(ph), fftop::blackScholes(.3), std::move(u), 0.0, 1.0);
+    std::vector<double> bad = {std::nan("")};
+    REQUIRE_APPROX(hoc(bad), 5000.0, 1e-15);
+  }
+  std::printf(failures ? "FAILED %d\n" : "ALL PASSED\n", failures);
+  return failures != 0;
+}

@@ -1,0 +1,154 @@
+"""GPU tests at BASELINE.json's full sizes: size-independent properties of the domain (put-call
+parity, batch invariance, determinism, early-exercise ordering, FFT round trip) plus sampled
+comparison against the oracle, and the C-ABI error behaviour."""
+import math
+
+import numpy as np
+import pytest
+
+from tests import cases as CASES
+from tests.conftest import assert_parity, assert_parity_tol, carr_madan_tolerance
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import fftoptionpricing_b200 as F
+    eng = F.Engine(0)
+    yield eng
+    eng.close()
+
+
+def test_c5_full_shard_properties(engine, best_oracle):
+    """125 000 sets x 8 maturities x 66 strikes (one GPU's share of config 5), device resident."""
+    import torch
+    P = 125_000
+    K, T = CASES.c5_strikes(), CASES.C5_T
+    prm_h = CASES.heston_batch(P)
+    prm = torch.tensor(prm_h, device="cuda:0")
+    call = torch.empty((P, 8, 66), dtype=torch.float64, device="cuda:0")
+    put = torch.empty_like(call)
+    engine.cos(0, 1, prm, K, 100.0, 0.03, T, 256, 0, out=call)
+    engine.cos(0, 1, prm, K, 100.0, 0.03, T, 256, 1, out=put)
+    engine.synchronize()
+    # put-call parity holds by construction of the reference (OptionPricing.h:378 vs :414):
+    # call - put = S0 - K e^{-rT}
+    disc = torch.exp(-0.03 * torch.tensor(T, device="cuda:0", dtype=torch.float64))
+    rhs = 100.0 - disc[None, :, None] * torch.tensor(K, device="cuda:0")[None, None, :]
+    assert float((call - put - rhs).abs().max()) < 1e-9
+    # sampled rows against the oracle
+    idx = np.array([0, 1, 17, 4095, 65536, 99999, 124999])
+    ref = best_oracle.cos(0, 1, prm_h[idx], K, 100.0, 0.03, T, 256, 0)
+    assert_parity(call[idx].cpu().numpy(), ref, what="C5 sampled sets vs oracle")
+    # batch invariance: a set's prices do not depend on its neighbours or its position in a tile
+    sub = torch.empty((16, 8, 66), dtype=torch.float64, device="cuda:0")
+    engine.cos(0, 1, prm[1003:1019].contiguous(), K, 100.0, 0.03, T, 256, 0, out=sub)
+    engine.synchronize()
+    assert torch.equal(sub, call[1003:1019])
+    # the fused loss is deterministic and equals the loss recomputed from the stored prices
+    mkt = ref[0]
+    w = CASES.c5_weights()
+    l1 = engine.cos_loss(0, 1, prm, K, 100.0, 0.03, T, 256, mkt, w)
+    l2 = engine.cos_loss(0, 1, prm, K, 100.0, 0.03, T, 256, mkt, w)
+    assert np.array_equal(l1, l2)
+    d = call.cpu().numpy() - mkt[None]
+    np.testing.assert_allclose(l1, (w[None] * d * d).sum(axis=(1, 2)) / (8 * 66), rtol=1e-12, atol=1e-300)
+
+
+def test_c2_batch_vs_oracle(engine, best_oracle):
+    P = 4096
+    prm = CASES.heston_batch(P)
+    K = CASES.fang_oost_strikes(-5.0, 5.0, 100.0, 1024)
+    out = engine.cos(0, 1, prm, K, 100.0, 0.0, [1.0], 256, 0)
+    idx = np.array([0, 5, 2047, 4095])
+    ref = best_oracle.cos(0, 1, prm[idx], K, 100.0, 0.0, [1.0], 256, 0)
+    assert_parity(out[idx], ref, what="C2 sampled sets vs oracle")
+
+
+def test_c3_american_put_batch(engine, best_oracle):
+    """Merton American put, N = 4096, 256 steps (config 3) on 300 sets: early-exercise ordering and
+    sampled parity."""
+    P = 300
+    prm = CASES.merton_batch(P)
+    am = engine.fsts(1, 0, prm, 4096, 7.5, 100.0, .05, .25, steps=256, american=True, payoff=1)
+    eu = engine.fsts(1, 0, prm, 4096, 7.5, 100.0, .05, .25, steps=256, american=False, payoff=1)
+    S = CASES.strike_underlying(-7.5, 7.5, 100.0, 4096)
+    pay = np.maximum(100.0 - S, 0.0)
+    assert np.all(am >= pay[None] - 1e-12)          # never below immediate exercise
+    # early exercise never lowers the value (checked away from the periodic wrap-around of the
+    # FFT grid, where the discrete operator is not monotone)
+    lo, hi = int(4096 * .3), int(4096 * .7)
+    # (sets with jump std > 0.7 wrap around the +-7.5 grid and violate it by up to 2e-4 in the
+    # oracle as well -- a property of the discretisation, not of the implementation)
+    assert np.all(am[:, lo:hi] >= eu[:, lo:hi] - 1e-3)
+    tame = prm[:, 3] < 0.5
+    assert np.all(am[tame][:, lo:hi] >= eu[tame][:, lo:hi] - 1e-6)
+    idx = np.array([0, 149, 299])
+    ref = best_oracle.fsts(1, 0, prm[idx], 4096, 7.5, 100.0, .05, .25, steps=256, american=True, payoff=1)
+    assert_parity(am[idx], ref, what="C3 sampled sets vs oracle")
+
+
+def test_c4_carr_madan_65536_batch(engine, best_oracle):
+    P, N = 48, 65536
+    prm = CASES.cgmy_batch(P)
+    call = engine.carr_madan(2, 0, prm, N, .25, 1.5, 500.0, .4, .25, False)
+    put = engine.carr_madan(2, 0, prm, N, .25, 1.5, 500.0, .4, .25, True)
+    Kc = CASES.carr_madan_strikes(N, .25, 500.0)
+    # put-call parity of the reference (OptionPricing.h:652): put = call - S0 + K e^{-rT}
+    rhs = -500.0 + Kc * math.exp(-.4 * .25)
+    lo, hi = int(N * .3), int(N * .7)
+    np.testing.assert_allclose((put - call)[:, lo:hi], np.broadcast_to(rhs[lo:hi], (P, hi - lo)),
+                               rtol=1e-12, atol=1e-7)
+    idx = np.array([0, 23, 47])
+    ref = best_oracle.carr_madan(2, 0, prm[idx], N, .25, 1.5, 500.0, .4, .25, False)
+    tol = carr_madan_tolerance(ref, N, .25, 1.5)
+    assert_parity_tol(call[idx], ref, tol, what="C4 sampled sets vs oracle")
+
+
+def test_objfn_population(engine, best_oracle):
+    P = 20000
+    prm = CASES.heston_batch(P)
+    u = np.linspace(-20, 20, 15)
+    ph = np.array([best_oracle.cf(0, 1, prm[0], 0.0, 1.0, complex(1.0, x))[1] for x in u])
+    loss = engine.objfn_cf(0, 1, prm, u, ph, 0.0, 1.0)
+    assert loss[0] < 1e-25                       # the generating set scores (numerically) zero
+    idx = np.array([1, 777, 19999])
+    np.testing.assert_allclose(loss[idx], best_oracle.objfn_cf(0, 1, prm[idx], u, ph, 0.0, 1.0),
+                               rtol=1e-10, atol=1e-12)
+    bad = prm[:4].copy()
+    bad[2, 0] = np.nan
+    out = engine.objfn_cf(0, 1, bad, u, ph, 0.0, 1.0)
+    assert out[2] == 5000.0 and np.all(np.isfinite(out))
+
+
+def test_error_behaviour(engine):
+    """Structural errors are reported as status codes with a message; nothing is silently fixed."""
+    import fftoptionpricing_b200 as F
+    with pytest.raises(F.FopError) as ei:
+        engine.carr_madan(0, 0, [.3], 1000, .25, 1.5, 50.0, .05, 1.0)   # N not a power of two
+    assert ei.value.status == 1
+    with pytest.raises(F.FopError) as ei:
+        engine.fsts(0, 1, CASES.heston0(), 1024, 5.0, 100.0, 0.0, 1.0, steps=8)  # time change + steps
+    assert ei.value.status == 4
+    with pytest.raises(F.FopError):
+        engine.cos(0, 0, [.3], [100.0], 100.0, .05, [1.0], 64, 0)       # fewer than two strikes
+    with pytest.raises(F.FopError):
+        engine.cos(0, 0, [.3], [200.0, 100.0, 50.0], 100.0, .05, [1.0], 4096, 0)  # numU too large
+    # empty batch is a no-op
+    assert engine.cos(0, 0, np.empty((0, 1)), [200.0, 100.0, 50.0], 100.0, .05, [1.0], 64, 0).shape == (0, 1, 3)
+    # NaN parameters propagate (the reference validates nothing)
+    out = engine.cos(0, 0, [float("nan")], [200.0, 100.0, 50.0], 100.0, .05, [1.0], 64, 0)
+    assert np.all(np.isnan(out))
+
+
+def test_ragged_tiles_and_many_maturities(engine, best_oracle):
+    """Row tiles that straddle parameter sets (M not dividing the tile), odd strike counts, numU
+    not a multiple of the chunk, single-row and single-set batches."""
+    for P, M, J, numU in [(1, 1, 3, 64), (7, 5, 67, 100), (33, 3, 130, 256), (3, 11, 9, 17)]:
+        prm = CASES.heston_batch(P)
+        K = np.concatenate([[5000.0], np.linspace(180.0, 40.0, J - 2), [.3]])
+        T = list(np.linspace(.1, 2.0, M))
+        got = engine.cos(0, 1, prm, K, 100.0, .02, T, numU, 0)
+        ref = best_oracle.cos(0, 1, prm, K, 100.0, .02, T, numU, 0)
+        assert_parity(got, ref, what=f"ragged P={P} M={M} J={J} numU={numU}")
