@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "cos_split_kernels.cuh"
@@ -23,12 +24,15 @@ const CosVariant kVariants[] = {
 };
 
 struct GemmVariant {
-  int TJ;
-  void (*kernel)(const CosGemmArgs);
+  int TJ;                                   // strike block JB = 4 TJ = 8 NB
+  void (*kernel)(const CosGemmArgs);        // DFMA register-tiled kernel (A/B knob FOP_COS_GEMM=dfma)
+  void (*dmma)(const CosGemmArgs);          // fp64 tensor-core kernel (default)
 };
-const GemmVariant kGemm[] = {{4, cos_gemm_kernel<4>},   {8, cos_gemm_kernel<8>},
-                             {12, cos_gemm_kernel<12>}, {16, cos_gemm_kernel<16>},
-                             {18, cos_gemm_kernel<18>}};
+const GemmVariant kGemm[] = {{4, cos_gemm_kernel<4>, cos_gemm_dmma_kernel<2>},
+                             {8, cos_gemm_kernel<8>, cos_gemm_dmma_kernel<4>},
+                             {12, cos_gemm_kernel<12>, cos_gemm_dmma_kernel<6>},
+                             {16, cos_gemm_kernel<16>, cos_gemm_dmma_kernel<8>},
+                             {18, cos_gemm_kernel<18>, cos_gemm_dmma_kernel<9>}};
 // strike-block width that wastes the fewest padded columns (ties -> wider block)
 const GemmVariant* pick_gemm(int J, int* nblk_out) {
   const GemmVariant* best = nullptr;
@@ -111,7 +115,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     gv = pick_gemm(J, &nblk);
     TJ = gv->TJ;
   }
-  const int JB = 4 * TJ, Jp = nblk * JB, KK = 2 * numU;
+  const int JB = 4 * TJ, Jp = nblk * JB;
+  // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
+  const int KK = fused ? 2 * numU : ((2 * numU + DM_KC - 1) / DM_KC) * DM_KC;
+  const bool use_dfma = getenv("FOP_COS_GEMM") && std::string(getenv("FOP_COS_GEMM")) == "dfma";
 
   // Strike-grid tables (u_k, V_k, strikes, maturities, cos/sin basis): rebuilt only when
   // (K_desc, S0, T, numU) change -- a calibration loop keeps them fixed while theta varies.
@@ -121,7 +128,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   auto& cc = h->cos_cache;
   const size_t tab_doubles = 2 * (size_t)numU + 2 * (size_t)J + M;
   const bool hit = cc.dev && cc.S0 == S0 && cc.numU == numU && cc.JB == JB && cc.Jp == Jp &&
-                   cc.K == Kh && cc.T == Th;
+                   cc.KK == KK && cc.K == Kh && cc.T == Th;
   if (!hit) {
     std::vector<double> tab(tab_doubles);
     double* uk = tab.data();
@@ -147,6 +154,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     }
     FOP_CUDA(h, cudaMemcpy(cc.dev, tab.data(), tab_doubles * 8, cudaMemcpyHostToDevice));
     const size_t boff = (tab_doubles + 1) & ~(size_t)1;  // 16-byte aligned basis
+    FOP_CUDA(h, cudaMemsetAsync(cc.dev + boff, 0, (size_t)KK * Jp * 8, h->stream));  // zero padding rows
     const int nb = numU * Jp;
     {
       ProfScope ps(h, "cos_basis_kernel");
@@ -154,7 +162,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
                                                                Jp, cc.dev + boff);
     }
     FOP_LAUNCH_CHECK(h);
-    cc.K = Kh;  cc.T = Th;  cc.S0 = S0;  cc.numU = numU;  cc.JB = JB;  cc.Jp = Jp;
+    cc.K = Kh;  cc.T = Th;  cc.S0 = S0;  cc.numU = numU;  cc.JB = JB;  cc.Jp = Jp;  cc.KK = KK;
   }
   const double* d_tab = cc.dev;
   const double* d_K = cc.dev + 2 * numU + J;
@@ -195,8 +203,9 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     L = cos_smem_layout(numU, v->TR, v->TJ, v->WR);
     FOP_CUDA(h, cudaFuncSetAttribute(v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   } else {
-    gemm_smem = cos_gemm_smem(TJ);
-    FOP_CUDA(h, cudaFuncSetAttribute(gv->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+    gemm_smem = use_dfma ? cos_gemm_smem(TJ) : cos_dmma_smem(TJ / 2);
+    FOP_CUDA(h, cudaFuncSetAttribute(use_dfma ? gv->kernel : gv->dmma,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
   }
 
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
@@ -224,8 +233,8 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     } else {
       CosCoeffArgs ca;
       ca.base = model.base;  ca.tc = model.time_change;  ca.greek = kind >> 1;
-      ca.P = pc;  ca.M = M;  ca.K = numU;  ca.np = np;
-      ca.spb = std::max(1, std::min(COEFF_MAX_SPB, 1024 / numU));
+      ca.P = pc;  ca.M = M;  ca.K = numU;  ca.Kp = KK / 2;  ca.np = np;
+      ca.spb = std::max(1, std::min(COEFF_MAX_SPB, 1024 / ca.Kp));
       ca.r = r;
       ca.params = d_params + (size_t)p0 * np;
       ca.T = d_T;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = d_C;
@@ -246,7 +255,8 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       const dim3 ggrid((unsigned)((rows + GEMM_RT - 1) / GEMM_RT), (unsigned)nblk);
       {
         ProfScope ps(h, "cos_gemm_kernel");
-        gv->kernel<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
+        if (use_dfma) gv->kernel<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
+        else gv->dmma<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
       }
       FOP_LAUNCH_CHECK(h);
     }

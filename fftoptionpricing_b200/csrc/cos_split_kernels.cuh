@@ -21,7 +21,7 @@ namespace fop {
 
 struct CosCoeffArgs {
   int base, tc, greek;
-  int P, M, K, np, spb;  // spb = parameter sets per block
+  int P, M, K, Kp, np, spb;  // Kp = padded u count (row stride of C = 2 Kp); spb = sets per block
   double r;
   const double* params;  // [P][np]
   const double* T;       // [M]
@@ -44,14 +44,19 @@ __global__ void __launch_bounds__(256) cos_coeff_kernel(const CosCoeffArgs a) {
     __syncthreads();
     if (tid < nsets) make_consts(a.base, a.tc, a.params + (size_t)(p0 + tid) * a.np, consts[tid]);
     __syncthreads();
-    for (int idx = tid; idx < nsets * K; idx += 256) {
-      const int s = idx / K, k = idx - s * K;
+    const int Kp = a.Kp;
+    for (int idx = tid; idx < nsets * Kp; idx += 256) {
+      const int s = idx / Kp, k = idx - s * Kp;
+      double2* crow = reinterpret_cast<double2*>(a.C) + (size_t)(p0 + s) * M * Kp + k;
+      if (k >= K) {  // zero padding so the contraction can run full stages
+        for (int m = 0; m < M; ++m) crow[(size_t)m * Kp] = make_double2(0.0, 0.0);
+        continue;
+      }
       const ModelConsts& mc = consts[s];
       const cd u = mk(0.0, __ldg(a.uk + k));
       const double v = __ldg(a.vk + k);
       CfPre pre;
       cf_prepare(a.base, a.tc, mc, u, a.r, pre);
-      double2* crow = reinterpret_cast<double2*>(a.C) + (size_t)(p0 + s) * M * K + k;
       int m = 0;
       for (; m + ILP <= M; m += ILP) {  // ILP independent maturities per trip
         cd d[ILP];
@@ -60,12 +65,12 @@ __global__ void __launch_bounds__(256) cos_coeff_kernel(const CosCoeffArgs a) {
 #pragma unroll
         for (int i = 0; i < ILP; ++i) d[i] = option_transform(a.greek, cexp(d[i]), u, a.r);
 #pragma unroll
-        for (int i = 0; i < ILP; ++i) crow[(size_t)(m + i) * K] = make_double2(d[i].x * v, d[i].y * v);
+        for (int i = 0; i < ILP; ++i) crow[(size_t)(m + i) * Kp] = make_double2(d[i].x * v, d[i].y * v);
       }
       for (; m < M; ++m) {
         const cd l = cf_log_at(a.tc, mc, pre, __ldg(a.T + m));
         const cd d = option_transform(a.greek, cexp(l), u, a.r);
-        crow[(size_t)m * K] = make_double2(d.x * v, d.y * v);
+        crow[(size_t)m * Kp] = make_double2(d.x * v, d.y * v);
       }
     }
   }
@@ -187,6 +192,143 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_kernel(const CosGemmArgs a) {
     for (int h = 0; h < TJH; ++h)
       *reinterpret_cast<double2*>(Es + (size_t)(arow + 8 * t) * JBP + 2 * cg + 8 * h) =
           make_double2(acc[t][2 * h], acc[t][2 * h + 1]);
+  __syncthreads();
+  for (int rr = warp; rr < nrows; rr += NT / 32) {
+    const long long row = row0 + rr;
+    const int m = (int)(row % a.M);
+    const double disc = exp(-a.r * __ldg(a.T + m));
+    double lsum = 0.0;
+    for (int jj = lane; jj < JB; jj += 32) {
+      const int j = blk * JB + jj;
+      if (j < a.J) {
+        const double o = cos_epilogue(a.kind, Es[(size_t)rr * JBP + jj], disc, __ldg(a.strikes + j),
+                                      a.S0, a.r);
+        if (a.out) a.out[(size_t)row * a.J + j] = o;
+        if (a.mkt) {
+          const double d = o - __ldg(a.mkt + (size_t)m * a.J + j);
+          lsum += (a.w ? __ldg(a.w + (size_t)m * a.J + j) : 1.0) * d * d;
+        }
+      }
+    }
+    if (a.rowloss) {
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+      if (lane == 0) a.rowloss[(size_t)row * a.nblk + blk] = lsum;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 tensor-core contraction (mma.sync.m8n8k4.f64, "DMMA").
+//
+// Why: ncu on the DFMA kernel above (profiles/r1_cos_c5_split_v1_ncu.json) shows it is
+// shared-memory bound -- every LDS.128 costs 4 wavefronts whether or not lanes broadcast, a
+// 4 x 18 register tile needs 22 x 16 B per lane per 144 FMAs = 1.22x the 128 B/clk the LSU can
+// deliver at the fp64 rate, and a tile large enough (8 x 18) does not fit in 255 registers.  The
+// MMA unit shares the A / B fragments across lanes in hardware: a 32 x 72 warp tile needs
+// 13 x 8 B per lane per 288 FMAs (0.36 B/FMA instead of 2.4), with the same 72 accumulators, and
+// DMMA issues at the full 64 FMA/clk/SM (37.1 vs 34.5 TFLOP/s measured for DFMA).
+//
+// Fragment layout of mma.m8n8k4 (g = lane / 4, c = lane % 4):
+//   A (8 x 4, row)  a     = A[g][c]
+//   B (4 x 8, col)  b     = B[c][g]
+//   C (8 x 8)       d0,d1 = C[g][2c], C[g][2c+1]
+constexpr int DM_KC = 32;            // kk per stage
+constexpr int DM_RT = 128;           // rows per CTA (4 warps x 32 rows)
+constexpr int DM_AS = DM_KC + 4;     // A row stride (288 B: rows shift by 32 B -> conflict free)
+
+__host__ __device__ constexpr int dm_bs(int NB) { return 8 * NB + 4; }  // B row stride (doubles)
+__host__ __device__ inline size_t cos_dmma_smem(int NB) {
+  const size_t stage = (size_t)DM_RT * DM_AS * 8 + (size_t)DM_KC * dm_bs(NB) * 8;
+  const size_t epi = (size_t)DM_RT * (8 * NB + 2) * 8;
+  return 2 * stage > epi ? 2 * stage : epi;
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// C rows are padded to KKp = multiple of DM_KC (zero filled), basis rows likewise, so every
+// stage is full and all loop bounds are compile-time constants.
+template <int NB>
+__global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs a) {
+  constexpr int JB = 8 * NB, JBP = JB + 2, BS = dm_bs(NB);
+  constexpr int NT = 128;
+  constexpr size_t A_BYTES = (size_t)DM_RT * DM_AS * 8;
+  constexpr size_t STAGE = A_BYTES + (size_t)DM_KC * BS * 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, c = lane & 3;
+  const long long row0 = (long long)blockIdx.x * DM_RT;
+  const int blk = blockIdx.y;
+  const int nrows = (int)min((long long)DM_RT, a.rows - row0);
+  const int KKp = a.KK;  // padded
+  const int nchunks = KKp / DM_KC;
+
+  auto issue = [&](int ch, int buf) {
+    double* As = reinterpret_cast<double*>(smem_raw + (size_t)buf * STAGE);
+    double* Bs = reinterpret_cast<double*>(smem_raw + (size_t)buf * STAGE + A_BYTES);
+    const int kk0 = ch * DM_KC;
+    constexpr int APC = DM_KC / 2;  // 16-byte pieces per A row
+#pragma unroll
+    for (int q = tid; q < DM_RT * APC; q += NT) {
+      const int rr = q / APC, pc = q % APC;
+      const int rsrc = rr < nrows ? rr : nrows - 1;  // clamp: rows past the end are never stored
+      cp_async16(As + rr * DM_AS + 2 * pc, a.C + (size_t)(row0 + rsrc) * KKp + kk0 + 2 * pc);
+    }
+    constexpr int BPC = JB / 2;
+    for (int q = tid; q < DM_KC * BPC; q += NT) {
+      const int rr = q / BPC, cc = q % BPC;
+      cp_async16(Bs + rr * BS + 2 * cc, a.basis + (size_t)(kk0 + rr) * a.Jp + (size_t)blk * JB + 2 * cc);
+    }
+    cp_async_commit();
+  };
+
+  double acc[4][NB][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int wrow = warp * 32;
+  issue(0, 0);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int buf = ch & 1;
+    if (ch + 1 < nchunks) {
+      issue(ch + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const double* As = reinterpret_cast<const double*>(smem_raw + (size_t)buf * STAGE) + (wrow + g) * DM_AS + c;
+    const double* Bs = reinterpret_cast<const double*>(smem_raw + (size_t)buf * STAGE + A_BYTES) + c * BS + g;
+#pragma unroll
+    for (int ks = 0; ks < DM_KC; ks += 4) {
+      double af[4], bf[NB];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = As[(8 * i) * DM_AS + ks];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) bf[j] = Bs[ks * BS + 8 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue through shared memory: one warp per row, lanes along strikes
+  double* Es = reinterpret_cast<double*>(smem_raw);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      *reinterpret_cast<double2*>(Es + (size_t)(wrow + 8 * i + g) * JBP + 8 * j + 2 * c) =
+          make_double2(acc[i][j][0], acc[i][j][1]);
   __syncthreads();
   for (int rr = warp; rr < nrows; rr += NT / 32) {
     const long long row = row0 + rr;

@@ -27,7 +27,7 @@ struct fop_handle_s {
   struct CosCache {
     std::vector<double> K, T;
     double S0 = 0;
-    int numU = 0, Jp = 0, JB = 0;
+    int numU = 0, Jp = 0, JB = 0, KK = 0;
     double* dev = nullptr;  // [uk | vk | x | K | T | basis]
     size_t bytes = 0;
   } cos_cache;
