@@ -250,15 +250,33 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// Output map of the reference entry points (OptionPricing.h:378,414,439,464,490,515,541) as
+//   out = (val - sub) * (disc * K * inv) + add      with per-kind uniform scalars
+struct CosEpi { double sub, inv, add; };
+__host__ __device__ inline CosEpi cos_epi_consts(int kind, double S0, double r) {
+  switch (kind) {
+    case 0: return {1.0, 1.0, S0};               // call price  (val-1) disc K + S0
+    case 1: return {0.0, 1.0, 0.0};              // put price    val disc K
+    case 2: return {0.0, 1.0 / S0, 1.0};         // call delta   val disc K / S0 + 1
+    case 3: return {0.0, 1.0 / S0, 0.0};         // put delta
+    case 4:
+    case 5: return {0.0, 1.0 / (S0 * S0), 0.0};  // gamma
+    case 6: return {r, 1.0, 0.0};                // call theta  (val - r) disc K
+    default: return {0.0, 1.0, 0.0};             // put theta
+  }
+}
+
 // C rows are padded to KKp = multiple of DM_KC (zero filled), basis rows likewise, so every
 // stage is full and all loop bounds are compile-time constants.
 template <int NB>
 __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs a) {
   constexpr int JB = 8 * NB, JBP = JB + 2, BS = dm_bs(NB);
-  constexpr int NT = 128;
   constexpr size_t A_BYTES = (size_t)DM_RT * DM_AS * 8;
   constexpr size_t STAGE = A_BYTES + (size_t)DM_KC * BS * 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_rowscale[DM_RT];  // disc(row) * inv
+  __shared__ int s_rowm[DM_RT];         // maturity index of the row
+  __shared__ double s_strike[JB];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, c = lane & 3;
@@ -267,25 +285,60 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs
   const int nrows = (int)min((long long)DM_RT, a.rows - row0);
   const int KKp = a.KK;  // padded
   const int nchunks = KKp / DM_KC;
+  const CosEpi epi = cos_epi_consts(a.kind, a.S0, a.r);
 
-  auto issue = [&](int ch, int buf) {
-    double* As = reinterpret_cast<double*>(smem_raw + (size_t)buf * STAGE);
-    double* Bs = reinterpret_cast<double*>(smem_raw + (size_t)buf * STAGE + A_BYTES);
-    const int kk0 = ch * DM_KC;
-    constexpr int APC = DM_KC / 2;  // 16-byte pieces per A row
+  // cp.async plan (fully coalesced: consecutive threads copy consecutive 16-byte pieces).
+  //   A: piece q = tid + 128 i  ->  row (tid >> 4) + 8 i, piece tid & 15 of the row's 256 B
+  //   B: piece q = tid + 128 i  ->  basis row q / BPC, piece q % BPC   (offsets precomputed)
+  constexpr int BPC = JB / 2;                      // 16-byte pieces per basis row
+  constexpr int NBI = (DM_KC * BPC + 127) / 128;   // B pieces per thread
+  const bool full = nrows == DM_RT;
+  const double* abase = a.C + (size_t)(row0 + (tid >> 4)) * KKp + 2 * (tid & 15);
+  double* adst = reinterpret_cast<double*>(smem_raw) + (tid >> 4) * DM_AS + 2 * (tid & 15);
+  int bsoff[NBI], bgoff[NBI];
 #pragma unroll
-    for (int q = tid; q < DM_RT * APC; q += NT) {
-      const int rr = q / APC, pc = q % APC;
-      const int rsrc = rr < nrows ? rr : nrows - 1;  // clamp: rows past the end are never stored
-      cp_async16(As + rr * DM_AS + 2 * pc, a.C + (size_t)(row0 + rsrc) * KKp + kk0 + 2 * pc);
+  for (int i = 0; i < NBI; ++i) {
+    const int q = tid + 128 * i;
+    const int rr = q / BPC, cc = q - rr * BPC;
+    bsoff[i] = q < DM_KC * BPC ? rr * BS + 2 * cc : -1;
+    bgoff[i] = rr * a.Jp + 2 * cc;
+  }
+  const double* bbase = a.basis + (size_t)blk * JB;
+  double* bdst = reinterpret_cast<double*>(smem_raw + A_BYTES);
+  auto issue = [&](int ch, int buf) {
+    const size_t so = (size_t)buf * (STAGE / 8);
+    const int kk0 = ch * DM_KC;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        cp_async16(adst + so + (8 * i) * DM_AS, abase + kk0 + (size_t)(8 * i) * KKp);
+    } else {  // last row tile: clamp the source row (rows past the end are never stored)
+#pragma unroll 1
+      for (int i = 0; i < 16; ++i) {
+        const int rr = (tid >> 4) + 8 * i;
+        const int rs = rr < nrows ? rr : nrows - 1;
+        cp_async16(adst + so + (8 * i) * DM_AS,
+                   a.C + (size_t)(row0 + rs) * KKp + kk0 + 2 * (tid & 15));
+      }
     }
-    constexpr int BPC = JB / 2;
-    for (int q = tid; q < DM_KC * BPC; q += NT) {
-      const int rr = q / BPC, cc = q % BPC;
-      cp_async16(Bs + rr * BS + 2 * cc, a.basis + (size_t)(kk0 + rr) * a.Jp + (size_t)blk * JB + 2 * cc);
-    }
+    const double* bs = bbase + (size_t)kk0 * a.Jp;
+#pragma unroll
+    for (int i = 0; i < NBI; ++i)
+      if (bsoff[i] >= 0) cp_async16(bdst + so + bsoff[i], bs + bgoff[i]);
     cp_async_commit();
   };
+  issue(0, 0);
+
+  // per-row / per-strike epilogue scalars (overlaps the first stage's latency)
+  if (tid < nrows) {
+    const int m = (int)((row0 + tid) % a.M);
+    s_rowm[tid] = m;
+    s_rowscale[tid] = exp(-a.r * __ldg(a.T + m)) * epi.inv;
+  }
+  if (tid < JB) {
+    const int j = blk * JB + tid;
+    s_strike[tid] = j < a.J ? __ldg(a.strikes + j) : 0.0;
+  }
 
   double acc[4][NB][2];
 #pragma unroll
@@ -294,7 +347,6 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs
     for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int wrow = warp * 32;
-  issue(0, 0);
   for (int ch = 0; ch < nchunks; ++ch) {
     const int buf = ch & 1;
     if (ch + 1 < nchunks) {
@@ -330,20 +382,26 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs
       *reinterpret_cast<double2*>(Es + (size_t)(wrow + 8 * i + g) * JBP + 8 * j + 2 * c) =
           make_double2(acc[i][j][0], acc[i][j][1]);
   __syncthreads();
-  for (int rr = warp; rr < nrows; rr += NT / 32) {
+  const int jvalid = min(JB, a.J - blk * JB);
+  constexpr int PASSES = (JB + 31) / 32;
+  for (int rr = warp; rr < nrows; rr += 4) {
     const long long row = row0 + rr;
-    const int m = (int)(row % a.M);
-    const double disc = exp(-a.r * __ldg(a.T + m));
+    const double rs = s_rowscale[rr];
+    const int m = s_rowm[rr];
+    const double* es = Es + (size_t)rr * JBP;
+    double* orow = a.out ? a.out + (size_t)row * a.J + (size_t)blk * JB : nullptr;
+    const double* mrow = a.mkt ? a.mkt + (size_t)m * a.J + (size_t)blk * JB : nullptr;
+    const double* wrw = a.w ? a.w + (size_t)m * a.J + (size_t)blk * JB : nullptr;
     double lsum = 0.0;
-    for (int jj = lane; jj < JB; jj += 32) {
-      const int j = blk * JB + jj;
-      if (j < a.J) {
-        const double o = cos_epilogue(a.kind, Es[(size_t)rr * JBP + jj], disc, __ldg(a.strikes + j),
-                                      a.S0, a.r);
-        if (a.out) a.out[(size_t)row * a.J + j] = o;
-        if (a.mkt) {
-          const double d = o - __ldg(a.mkt + (size_t)m * a.J + j);
-          lsum += (a.w ? __ldg(a.w + (size_t)m * a.J + j) : 1.0) * d * d;
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      const int jj = lane + 32 * ps;
+      if (jj < jvalid) {
+        const double o = fma(es[jj] - epi.sub, rs * s_strike[jj], epi.add);
+        if (orow) orow[jj] = o;
+        if (mrow) {
+          const double d = o - __ldg(mrow + jj);
+          lsum = fma((wrw ? __ldg(wrw + jj) : 1.0) * d, d, lsum);
         }
       }
     }
