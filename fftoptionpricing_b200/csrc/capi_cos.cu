@@ -242,7 +242,8 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       const int cgrid = std::min(ngroups, h->sm_count * 32);
       {
         ProfScope ps(h, "cos_coeff_kernel");
-        if (M >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
+        if (M >= 4) cos_coeff_kernel<4><<<cgrid, 256, 0, h->stream>>>(ca);
+        else if (M >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
         else cos_coeff_kernel<1><<<cgrid, 256, 0, h->stream>>>(ca);
       }
       FOP_LAUNCH_CHECK(h);

@@ -142,11 +142,19 @@ __device__ __forceinline__ void cf_prepare(int base, int tc, const ModelConsts& 
   pre.pod = cdiv(psi, delta);
 }
 
-// log phi(u) at maturity T
-__device__ __forceinline__ cd cf_log_at(int tc, const ModelConsts& c, const CfPre& pre, double T) {
-  cd l = mk(pre.lin.x * T, pre.lin.y * T);
-  if (tc == TC_NONE) return l;
-  if (c.adaV == 0.0) {
+// log phi(u) at maturity T, straight-line variants (no data-dependent branch) so that several
+// maturities of one (set, u) pair interleave:
+//   CF_MODE_LEVY  no time change          CF_MODE_CIR  CIR clock, adaV != 0
+//   CF_MODE_DET   deterministic clock (adaV == 0, test.cpp:1187)
+enum { CF_MODE_LEVY = 0, CF_MODE_CIR = 1, CF_MODE_DET = 2 };
+__device__ __forceinline__ int cf_mode(int tc, const ModelConsts& c) {
+  return tc == TC_NONE ? CF_MODE_LEVY : (c.adaV == 0.0 ? CF_MODE_DET : CF_MODE_CIR);
+}
+template <int MODE>
+__device__ __forceinline__ cd cf_log_at_mode(const ModelConsts& c, const CfPre& pre, double T) {
+  const cd l = mk(pre.lin.x * T, pre.lin.y * T);
+  if (MODE == CF_MODE_LEVY) return l;
+  if (MODE == CF_MODE_DET) {
     const cd kp = pre.delta, ps = pre.pod;
     const cd ek = 1.0 - cexp(mk(-kp.x * T, -kp.y * T));
     const cd ekk = cdiv(ek, kp);
@@ -162,17 +170,23 @@ __device__ __forceinline__ cd cf_log_at(int tc, const ModelConsts& c, const CfPr
   const cd cc = mk(c.aos2 * (2.0 * lw.x + pre.dmk.x * T), c.aos2 * (2.0 * lw.y + pre.dmk.y * T));
   return l - (c.v0 * b) - cc;
 }
+__device__ __forceinline__ cd cf_log_at(int tc, const ModelConsts& c, const CfPre& pre, double T) {
+  const int mode = cf_mode(tc, c);
+  if (mode == CF_MODE_LEVY) return cf_log_at_mode<CF_MODE_LEVY>(c, pre, T);
+  if (mode == CF_MODE_DET) return cf_log_at_mode<CF_MODE_DET>(c, pre, T);
+  return cf_log_at_mode<CF_MODE_CIR>(c, pre, T);
+}
 
 // Option transforms applied to phi(u) (OptionPricing.h:44-73): 0 price, 1 delta, 2 gamma, 3 theta
 __device__ __forceinline__ cd option_transform(int greek, cd phi, cd u, double r) {
   if (greek == 0) return phi;
   if (greek == 1) return phi * u;
   if (greek == 2) return -(phi * (u * (1.0 - u)));
-  if (phi.x > 0.0) {  // theta; log of the CF VALUE (principal branch), as the reference does
-    const cd l = clog(phi);
-    return -(mk(l.x - r, l.y) * phi);
-  }
-  return mk(0.0, 0.0);
+  // theta; log of the CF VALUE (principal branch), as the reference does; select, not branch
+  const cd l = clog(phi);
+  const cd t = -(mk(l.x - r, l.y) * phi);
+  const bool pos = phi.x > 0.0;
+  return mk(pos ? t.x : 0.0, pos ? t.y : 0.0);
 }
 
 }  // namespace fop

@@ -32,6 +32,28 @@ struct CosCoeffArgs {
 
 constexpr int COEFF_MAX_SPB = 64;
 
+// all maturities of one (set, u) pair, ILP at a time as one straight-line block
+template <int MODE, int ILP>
+__device__ __forceinline__ void coeff_maturities(const CosCoeffArgs& a, const ModelConsts& mc,
+                                                 const CfPre& pre, cd u, double v, double2* crow,
+                                                 int Kp) {
+  const int M = a.M;
+  int m = 0;
+  for (; m + ILP <= M; m += ILP) {
+    cd d[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) d[i] = cf_log_at_mode<MODE>(mc, pre, __ldg(a.T + m + i));
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) d[i] = option_transform(a.greek, cexp(d[i]), u, a.r);
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) crow[(size_t)(m + i) * Kp] = make_double2(d[i].x * v, d[i].y * v);
+  }
+  for (; m < M; ++m) {
+    const cd d = option_transform(a.greek, cexp(cf_log_at_mode<MODE>(mc, pre, __ldg(a.T + m))), u, a.r);
+    crow[(size_t)m * Kp] = make_double2(d.x * v, d.y * v);
+  }
+}
+
 template <int ILP>
 __global__ void __launch_bounds__(256) cos_coeff_kernel(const CosCoeffArgs a) {
   __shared__ ModelConsts consts[COEFF_MAX_SPB];
@@ -57,21 +79,10 @@ __global__ void __launch_bounds__(256) cos_coeff_kernel(const CosCoeffArgs a) {
       const double v = __ldg(a.vk + k);
       CfPre pre;
       cf_prepare(a.base, a.tc, mc, u, a.r, pre);
-      int m = 0;
-      for (; m + ILP <= M; m += ILP) {  // ILP independent maturities per trip
-        cd d[ILP];
-#pragma unroll
-        for (int i = 0; i < ILP; ++i) d[i] = cf_log_at(a.tc, mc, pre, __ldg(a.T + m + i));
-#pragma unroll
-        for (int i = 0; i < ILP; ++i) d[i] = option_transform(a.greek, cexp(d[i]), u, a.r);
-#pragma unroll
-        for (int i = 0; i < ILP; ++i) crow[(size_t)(m + i) * Kp] = make_double2(d[i].x * v, d[i].y * v);
-      }
-      for (; m < M; ++m) {
-        const cd l = cf_log_at(a.tc, mc, pre, __ldg(a.T + m));
-        const cd d = option_transform(a.greek, cexp(l), u, a.r);
-        crow[(size_t)m * Kp] = make_double2(d.x * v, d.y * v);
-      }
+      const int mode = cf_mode(a.tc, mc);
+      if (mode == CF_MODE_CIR) coeff_maturities<CF_MODE_CIR, ILP>(a, mc, pre, u, v, crow, Kp);
+      else if (mode == CF_MODE_LEVY) coeff_maturities<CF_MODE_LEVY, ILP>(a, mc, pre, u, v, crow, Kp);
+      else coeff_maturities<CF_MODE_DET, 1>(a, mc, pre, u, v, crow, Kp);
     }
   }
 }
