@@ -173,6 +173,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use every
+    # host core (set before libgomp is loaded with the oracle library)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     steps, warm = args.steps, args.warmup
     first = cpu_reference_rate(seconds_target=2.0)
     # size each step for ~2 s so the whole run stays within a few minutes
@@ -348,11 +351,22 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(args.cpu_seconds).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
     eng.close()
+    if world > 1:
+        # tear down explicitly and leave without running interpreter finalisers: NCCL / CUDA
+        # teardown order at interpreter exit is not ours to control and must not turn a finished
+        # measurement into a non-zero exit code
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

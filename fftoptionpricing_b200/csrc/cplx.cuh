@@ -59,7 +59,7 @@ __host__ __device__ __forceinline__ cd clog(cd z) {
   const double sc = fm_make((1023 - e) << 20, 0);  // 2^-e, exact
   const double xs = z.x * sc, ys = z.y * sc;
   const double n = fm_fma(xs, xs, ys * ys);
-  const double lr = fm_fma((double)e, 0.69314718055994530942, 0.5 * fm_log_pos(n));
+  const double lr = fm_fma((double)e, FM_TAB(fm_k)[16], 0.5 * fm_log_pos(n));
   return mk(big == 0.0 ? -INFINITY : lr, fm_atan2(z.y, z.x));
 }
 // principal square root (Re >= 0; on the negative real axis the sign of Im follows the sign of z.y)

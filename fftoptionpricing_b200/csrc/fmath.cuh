@@ -54,6 +54,26 @@ FM_TABLE(fm_atan_t, 1.62858201153657823623e-02, -3.65315727442169155270e-02,
          -7.69187620504482999495e-02, 9.09088713343650656196e-02, -1.11111104054623557880e-01,
          1.42857142725034663711e-01, -1.99999999998764832476e-01, 3.33333333333329318027e-01)
 
+// scalar constants whose low 32 bits are non-zero (not encodable as DFMA immediates): kept in the
+// constant bank as well so that no UMOV pair is needed to materialise them
+FM_TABLE(fm_k, 1.4426950408889634,        // 0  log2(e)
+         -6.93147180559945286e-01,        // 1  -ln2 hi
+         -2.31904681384629956e-17,        // 2  -ln2 lo
+         6.36619772367581382e-01,         // 3  2/pi
+         -1.57079632679489656e+00,        // 4  -pi/2 hi
+         -6.12323399573676604e-17,        // 5  -pi/2 mid
+         1.49738490485916983e-33,         // 6  +|pi/2 lo|
+         6.93147180369123816490e-01,      // 7  ln2_hi (fdlibm split)
+         1.90821492927058770002e-10,      // 8  ln2_lo (fdlibm split)
+         0.41421356237309503,             // 9  tan(pi/8)
+         7.85398163397448279e-01,         // 10 pi/4 hi
+         3.06161699786838302e-17,         // 11 pi/4 lo
+         1.57079632679489656e+00,         // 12 pi/2 hi
+         6.12323399573676604e-17,         // 13 pi/2 lo
+         3.14159265358979312e+00,         // 14 pi hi
+         1.22464679914735321e-16,         // 15 pi lo
+         0.69314718055994530942)          // 16 ln2
+
 #define FM_HD __host__ __device__ __forceinline__
 
 FM_HD int fm_hi(double x) {
@@ -101,14 +121,15 @@ FM_HD double fm_div(double a, double b) {
 }
 
 FM_HD double fm_exp(double x) {
+  const double* K = FM_TAB(fm_k);
   x = x < -746.0 ? -746.0 : x;  // selects keep NaN
   x = x > 710.0 ? 710.0 : x;
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-  const double t = fm_fma(x, 1.4426950408889634, MAGIC);
+  const double t = fm_fma(x, K[0], MAGIC);
   const int k = fm_lo(t);
   const double kd = t - MAGIC;
-  double r = fm_fma(kd, -6.93147180559945286e-01, x);   // ln2 hi
-  r = fm_fma(kd, -2.31904681384629956e-17, r);          // ln2 lo
+  double r = fm_fma(kd, K[1], x);   // ln2 hi
+  r = fm_fma(kd, K[2], r);   // ln2 lo
   const double* c = FM_TAB(fm_exp_q);
   double q = c[0];
 #pragma unroll
@@ -121,13 +142,14 @@ FM_HD double fm_exp(double x) {
 
 // sin and cos of x, |x| < 2^30
 FM_HD void fm_sincos(double x, double* sn, double* cs) {
+  const double* K = FM_TAB(fm_k);
   const double MAGIC = 6755399441055744.0;
-  const double t = fm_fma(x, 6.36619772367581382e-01, MAGIC);  // 2/pi
+  const double t = fm_fma(x, K[3], MAGIC);  // 2/pi
   const int q = fm_lo(t);
   const double qd = t - MAGIC;
-  double r = fm_fma(qd, -1.57079632679489656e+00, x);   // pi/2 in three parts
-  r = fm_fma(qd, -6.12323399573676604e-17, r);
-  r = fm_fma(qd, 1.49738490485916983e-33, r);
+  double r = fm_fma(qd, K[4], x);   // pi/2 in three parts
+  r = fm_fma(qd, K[5], r);
+  r = fm_fma(qd, K[6], r);
   const double z = r * r;
   const double* S = FM_TAB(fm_sin_s);
   const double* C = FM_TAB(fm_cos_c);
@@ -150,6 +172,7 @@ FM_HD void fm_sincos(double x, double* sn, double* cs) {
 
 // log(x), x > 0 and normal (callers scale; no special cases)
 FM_HD double fm_log_pos(double x) {
+  const double* K = FM_TAB(fm_k);
   int hx = fm_hi(x);
   const int lx = fm_lo(x);
   const int k = (hx - 0x3fe6a09e) >> 20;  // x = 2^k m, m in [sqrt(1/2), sqrt(2))
@@ -166,12 +189,12 @@ FM_HD double fm_log_pos(double x) {
   const double hfsq = 0.5 * f * f;
   const double dk = (double)k;
   // k ln2_hi - ((hfsq - (s (hfsq + R) + k ln2_lo)) - f)
-  return fm_fma(dk, 6.93147180369123816490e-01,
-                -((hfsq - fm_fma(s, hfsq + R, dk * 1.90821492927058770002e-10)) - f));
+  return fm_fma(dk, K[7], -((hfsq - fm_fma(s, hfsq + R, dk * K[8])) - f));
 }
 
 // atan2(y, x), finite arguments; (0, 0) -> 0 or pi like the C library
 FM_HD double fm_atan2(double y, double x) {
+  const double* K = FM_TAB(fm_k);
   double ax = fabs(x), ay = fabs(y);
   // bring tiny (incl. subnormal: rcp.approx flushes them) or huge pairs into the safe range;
   // powers of two, so the ratio is unchanged
@@ -180,7 +203,7 @@ FM_HD double fm_atan2(double y, double x) {
   ax *= sc;
   ay *= sc;
   const double mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
-  const bool big = mn > 0.41421356237309503 * mx;  // tan(pi/8)
+  const bool big = mn > K[9] * mx;  // tan(pi/8)
   const double num = big ? mn - mx : mn;
   double den = big ? mn + mx : mx;
   den = den == 0.0 ? 1.0 : den;  // atan2(0, 0): t = 0
@@ -192,9 +215,9 @@ FM_HD double fm_atan2(double y, double x) {
   for (int i = 1; i < 11; ++i) p = fm_fma(p, z, A[i]);
   double a = fm_fma(-t, z * p, t);
   // + pi/4 (hi + lo) when reduced
-  a = big ? (7.85398163397448279e-01 + (a + 3.06161699786838302e-17)) : a;
-  a = ay > ax ? (1.57079632679489656e+00 - (a - 6.12323399573676604e-17)) : a;
-  a = fm_hi(x) < 0 ? (3.14159265358979312e+00 - (a - 1.22464679914735321e-16)) : a;
+  a = big ? (K[10] + (a + K[11])) : a;
+  a = ay > ax ? (K[12] - (a - K[13])) : a;
+  a = fm_hi(x) < 0 ? (K[14] - (a - K[15])) : a;
   return fm_hi(y) < 0 ? -a : a;
 }
 
