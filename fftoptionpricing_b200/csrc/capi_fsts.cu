@@ -31,9 +31,18 @@ __host__ __device__ inline size_t fsts_slot_bytes(int n) {
   return (size_t)fft_padded_size(N) * sizeof(cd) + (size_t)N * 8;
 }
 
+// Register-resident time loop.  Thread b of a set owns, at every step boundary, the 16 real values
+// at positions b + S0 t (S0 = N/16) -- exactly the operands of the first forward pass and the
+// results of the last inverse pass, so nothing is stored between steps.  Per step:
+//   fwd pass 0 (regs -> smem) | middle passes (smem <-> regs) | last pass + multiply + first
+//   inverse pass fused in registers | inverse middle passes | inverse pass 0 (smem -> regs) + max.
+// Twiddles: one base W_L^q per radix-16 pass kept in registers, its powers by a depth-4 tree.
+template <int LOGN>
 __global__ void __launch_bounds__(256) fsts_kernel(const FstsArgs a, const double2* __restrict__ tw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = a.n, N = 1 << n, T = N >> 4;
+  // N is a template parameter: every stride, padded offset and pass count below is a compile-time
+  // constant, so the time loop contains no integer division and addresses are base + immediate
+  constexpr int n = LOGN, N = 1 << n, T = N >> 4;
   const int tpb = fft_single_tpb(n);
   const int slot = threadIdx.x / T, b = threadIdx.x - slot * T;
   const size_t slot_bytes = fsts_slot_bytes(n);
@@ -49,6 +58,23 @@ __global__ void __launch_bounds__(256) fsts_kernel(const FstsArgs a, const doubl
   const int greek = a.kind == 0 ? 0 : a.kind == 1 ? 1 : a.kind == 2 ? 2 : 3;
   const double scale = a.disc / (double)N;
 
+  // plan: np16 radix-16 passes with strides S_p = N >> 4(p+1); when the last radix is 16 the
+  // final one (S = 1) is the fused register pass, otherwise a small radix-rl pass is.
+  constexpr int rl = (n & 3) == 0 ? 16 : (1 << (n & 3));
+  constexpr int np16 = ((n + 3) >> 2) - (rl == 16 ? 0 : 1);
+  constexpr int nsm = rl == 16 ? np16 - 1 : np16;  // radix-16 passes that go through shared memory
+  constexpr int S0 = N >> 4;
+  // twiddle bases (forward sign) of the shared-memory passes: w[p] = W_{16 S_p}^{b mod S_p}
+  cd w[3];
+  int base[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    constexpr int SS[3] = {N >> 4 > 0 ? N >> 4 : 1, N >> 8 > 0 ? N >> 8 : 1, N >> 12 > 0 ? N >> 12 : 1};
+    const int S = SS[p];
+    w[p] = p < nsm ? tw_load<-1>(tw, (b % S) * (N / (S << 4))) : mk(1.0, 0.0);
+    base[p] = fft_base16(b, S);
+  }
+
   for (int p0 = blockIdx.x * tpb; p0 < a.P; p0 += gridDim.x * tpb) {
     const int cnt = min(tpb, a.P - p0);
     const bool live = slot < cnt;
@@ -57,16 +83,16 @@ __global__ void __launch_bounds__(256) fsts_kernel(const FstsArgs a, const doubl
       make_consts(a.base, a.tc, a.params + (size_t)(p0 + threadIdx.x) * a.np, consts[threadIdx.x]);
     __syncthreads();
 
-    // multiplier m at digit-reversed positions: computed one CF per loop trip into the (still
-    // unused) value grid, then each thread pulls its 16 positions 16 b .. 16 b + 15 into registers
+    // multiplier m at digit-reversed positions: one CF per loop trip into the (still unused)
+    // value grid, then each thread pulls its 16 positions 16 b .. 16 b + 15 into registers
     {
       const ModelConsts& mc = consts[slot];
 #pragma unroll 1
       for (int pos = b; pos < N; pos += T) {
         const int k = fft_inv_pos(pos, n);
-        double w = du * k;
-        if (w > vmax) w -= 2.0 * vmax;  // getUDomain, OptionPricing.h:19-23 (strict >)
-        const cd u = mk(0.0, w);
+        double wk = du * k;
+        if (wk > vmax) wk -= 2.0 * vmax;  // getUDomain, OptionPricing.h:19-23 (strict >)
+        const cd u = mk(0.0, wk);
         CfPre pre;
         cf_prepare(a.base, a.tc, mc, u, a.r, pre);
         const cd phi = cexp(cf_log_at(a.tc, mc, pre, a.Tcf));
@@ -81,45 +107,86 @@ __global__ void __launch_bounds__(256) fsts_kernel(const FstsArgs a, const doubl
     // payoff on the log-asset grid x_j = -xmax + dx j, asset = strike e^{x_j}
     for (int j = b; j < N; j += T) {
       const double s = a.strike * exp(-a.xmax + dx * j);
-      const double pv = a.payoff == 1 ? (s < a.strike ? a.strike - s : 0.0)
-                                      : (s > a.strike ? s - a.strike : 0.0);
-      pay[j] = pv;
-      sm[fft_pad(j)] = mk(pv, 0.0);
+      pay[j] = a.payoff == 1 ? (s < a.strike ? a.strike - s : 0.0) : (s > a.strike ? s - a.strike : 0.0);
     }
     __syncthreads();
+    double vre[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) vre[t] = pay[b + S0 * t];
 
     // Idle slots of a tail block run the same instruction stream on their own (garbage) shared
     // memory so that every thread reaches every barrier; only global traffic is predicated.
-    const int np = fft_num_passes(n);
     for (int st = 0; st < a.steps; ++st) {
-      for (int ps = 0; ps < np; ++ps) {
-        fft_dif_pass<-1>(sm, b, n, ps, tw);
-        __syncthreads();
-      }
-      {
-        cd x[16];
-        load16(sm, 16 * b, 1, x);
+      cd x[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = x[i] * mult[i];
-        store16(sm, 16 * b, 1, x);
-      }
-      __syncthreads();
-      for (int ps = 0; ps < np; ++ps) {
-        fft_dit_pass<1>(sm, b, n, ps, tw);
+      for (int t = 0; t < 16; ++t) x[t] = mk(vre[t], 0.0);
+      // ---- forward passes through shared memory
+      if (nsm >= 1) {
+        dif16_regs_pow<-1>(x, w[0]);
+        store16_dft<-1>(sm, b, S0, x);
         __syncthreads();
+#pragma unroll
+        for (int p = 1; p < nsm; ++p) {
+          const int S = N >> (4 * (p + 1));
+          load16(sm, base[p], S, x);
+          dif16_regs_pow<-1>(x, w[p]);
+          store16_dft<-1>(sm, base[p], S, x);
+          __syncthreads();
+        }
+        load16(sm, 16 * b, 1, x);
       }
-      for (int j = b; j < N; j += T) {
-        double v = sm[fft_pad(j)].x;
-        if (a.american) v = fmax(v, pay[j]);
-        sm[fft_pad(j)] = mk(v, 0.0);
+      // ---- last forward pass, multiply, first inverse pass: all on the thread's 16 points
+      if (rl == 16) {
+        Dft<16, -1>::run(x);
+        cd y[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) y[k] = x[Dft<16, -1>::out(k)] * mult[k];
+        Dft<16, 1>::run(y);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = y[Dft<16, 1>::out(k)];
+      } else {
+        if (rl == 8) last_pass_regs<8, -1>(x);
+        else if (rl == 4) last_pass_regs<4, -1>(x);
+        else last_pass_regs<2, -1>(x);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = x[k] * mult[k];
+        if (rl == 8) last_pass_regs<8, 1>(x);
+        else if (rl == 4) last_pass_regs<4, 1>(x);
+        else last_pass_regs<2, 1>(x);
       }
-      __syncthreads();
+      // ---- inverse passes through shared memory (ascending stride), last one into registers
+      if (nsm >= 1) {
+        store16(sm, 16 * b, 1, x);
+        __syncthreads();
+#pragma unroll
+        for (int p = nsm - 1; p >= 1; --p) {
+          const int S = N >> (4 * (p + 1));
+          load16(sm, base[p], S, x);
+          dit16_regs_pow<1>(x, conj(w[p]));
+          store16_dft<1>(sm, base[p], S, x);
+          __syncthreads();
+        }
+        load16(sm, b, S0, x);
+        dit16_regs_pow<1>(x, conj(w[0]));
+#pragma unroll
+        for (int k = 0; k < 16; ++k) vre[k] = x[Dft<16, 1>::out(k)].x;
+        // no barrier: the next step's first pass rewrites exactly the positions this thread just read
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) vre[k] = x[k].x;
+      }
+      if (a.american) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) vre[k] = fmax(vre[k], pay[b + S0 * k]);
+      }
     }
 
     if (live) {
       double* o = a.out + (size_t)(p0 + slot) * N;
-      for (int j = b; j < N; j += T) {
-        double v = sm[fft_pad(j)].x;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int j = b + S0 * k;
+        double v = vre[k];
         if (a.kind == 1 || a.kind == 2) {  // delta, gamma: divide by the asset (OptionPricing.h:226,275)
           const double s = a.strike * exp(-a.xmax + dx * j);
           v = a.kind == 1 ? v / s : v / (s * s);
@@ -177,12 +244,24 @@ extern "C" int fop_fsts(fop_handle_t h, fop_model_t model, const double* params,
   a.params = d_params;  a.out = d_out;
   const int tpb = fft_single_tpb(n);
   const size_t smem = (size_t)tpb * fsts_slot_bytes(n) + (size_t)tpb * sizeof(ModelConsts);
-  FOP_CUDA(h, cudaFuncSetAttribute(fsts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void (*kern)(const FstsArgs, const double2*) = nullptr;
+  switch (n) {
+    case 4: kern = fsts_kernel<4>; break;
+    case 5: kern = fsts_kernel<5>; break;
+    case 6: kern = fsts_kernel<6>; break;
+    case 7: kern = fsts_kernel<7>; break;
+    case 8: kern = fsts_kernel<8>; break;
+    case 9: kern = fsts_kernel<9>; break;
+    case 10: kern = fsts_kernel<10>; break;
+    case 11: kern = fsts_kernel<11>; break;
+    default: kern = fsts_kernel<12>; break;
+  }
+  FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int groups = (P + tpb - 1) / tpb;
   const int grid = std::min(groups, h->sm_count * 4);
   {
     ProfScope ps(h, "fsts_kernel");
-    fsts_kernel<<<grid, fft_single_threads(n), smem, h->stream>>>(a, tw);
+    kern<<<grid, fft_single_threads(n), smem, h->stream>>>(a, tw);
   }
   FOP_LAUNCH_CHECK(h);
   if (out_host) {

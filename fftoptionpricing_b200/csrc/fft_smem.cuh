@@ -248,19 +248,24 @@ FOP_HD void last_pass_regs(cd* x) {
 }
 
 // shared-memory <-> register moves for a radix-16 pass (stride S) and for the consecutive pass
+// When S is a multiple of 16, pad(base + t S) = pad(base) + t (S + S/16): one padded base plus
+// constant offsets (immediates once S is a compile-time constant).
+FOP_HD int fft_pad_off(int base, int t, int S) {
+  return (S & 15) == 0 ? fft_pad(base) + t * (S + (S >> 4)) : fft_pad(base + t * S);
+}
 FOP_HD void load16(const cd* sm, int base, int S, cd* x) {
 #pragma unroll
-  for (int t = 0; t < 16; ++t) x[t] = sm[fft_pad(base + t * S)];
+  for (int t = 0; t < 16; ++t) x[t] = sm[fft_pad_off(base, t, S)];
 }
 // stores the k-th output (held in x[perm(k)]) to base + k S
 template <int SIGN>
 FOP_HD void store16_dft(cd* sm, int base, int S, const cd* x) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k) sm[fft_pad(base + k * S)] = x[Dft<16, SIGN>::out(k)];
+  for (int k = 0; k < 16; ++k) sm[fft_pad_off(base, k, S)] = x[Dft<16, SIGN>::out(k)];
 }
 FOP_HD void store16(cd* sm, int base, int S, const cd* x) {
 #pragma unroll
-  for (int t = 0; t < 16; ++t) sm[fft_pad(base + t * S)] = x[t];
+  for (int t = 0; t < 16; ++t) sm[fft_pad_off(base, t, S)] = x[t];
 }
 // after dit16 the outputs are also permuted: natural k-th output in x[out(k)]
 template <int SIGN>
