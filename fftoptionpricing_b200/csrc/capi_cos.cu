@@ -11,69 +11,26 @@
 namespace {
 using namespace fop;
 
-struct CosVariant {
-  int TR, TJ, WR;
-  void (*kernel)(const CosArgs);
-};
-#define COS_V(TR, TJ, WR) \
-  { TR, TJ, WR, cos_kernel<TR, TJ, WR> }
-const CosVariant kVariants[] = {
-    COS_V(4, 4, 1),  COS_V(4, 8, 1),  COS_V(4, 12, 1), COS_V(4, 16, 1), COS_V(4, 18, 1),
-    COS_V(2, 16, 2), COS_V(2, 18, 2),
-    COS_V(2, 16, 1), COS_V(2, 18, 1), COS_V(1, 16, 1),
-};
-
 struct GemmVariant {
-  int TJ;                                   // strike block JB = 4 TJ = 8 NB
-  void (*kernel)(const CosGemmArgs);        // DFMA register-tiled kernel (A/B knob FOP_COS_GEMM=dfma)
-  void (*dmma)(const CosGemmArgs);          // fp64 tensor-core kernel (default)
+  int NB;                             // strike block JB = 8 NB columns (NB n-blocks of the MMA)
+  void (*dmma)(const CosGemmArgs);    // fp64 tensor-core contraction
 };
-const GemmVariant kGemm[] = {{4, cos_gemm_kernel<4>, cos_gemm_dmma_kernel<2>},
-                             {8, cos_gemm_kernel<8>, cos_gemm_dmma_kernel<4>},
-                             {12, cos_gemm_kernel<12>, cos_gemm_dmma_kernel<6>},
-                             {16, cos_gemm_kernel<16>, cos_gemm_dmma_kernel<8>},
-                             {18, cos_gemm_kernel<18>, cos_gemm_dmma_kernel<9>}};
+const GemmVariant kGemm[] = {{2, cos_gemm_dmma_kernel<2>}, {4, cos_gemm_dmma_kernel<4>},
+                             {6, cos_gemm_dmma_kernel<6>}, {8, cos_gemm_dmma_kernel<8>},
+                             {9, cos_gemm_dmma_kernel<9>}};
 // strike-block width that wastes the fewest padded columns (ties -> wider block)
 const GemmVariant* pick_gemm(int J, int* nblk_out) {
   const GemmVariant* best = nullptr;
   long long best_cost = 0;
   for (const GemmVariant& v : kGemm) {
-    const int JB = 4 * v.TJ, nblk = (J + JB - 1) / JB;
+    const int JB = 8 * v.NB, nblk = (J + JB - 1) / JB;
     const long long cost = (long long)nblk * JB;
-    if (!best || cost < best_cost || (cost == best_cost && v.TJ > best->TJ)) {
+    if (!best || cost < best_cost || (cost == best_cost && v.NB > best->NB)) {
       best = &v;
       best_cost = cost;
       *nblk_out = nblk;
     }
   }
-  return best;
-}
-
-// pick the strike-block width that wastes the fewest padded columns, then the largest row tile
-// whose shared-memory footprint fits
-const CosVariant* pick_variant(fop_handle_t h, int K, int J, int* nblk_out) {
-  int want_tr = 0, want_wr = 0;
-  if (const char* e = getenv("FOP_COS_VARIANT")) {  // tuning knob: "TR,WR", e.g. "2,2"
-    sscanf(e, "%d,%d", &want_tr, &want_wr);
-  }
-  const CosVariant* best = nullptr;
-  long long best_cost = 0;
-  int best_nblk = 0;
-  for (const CosVariant& v : kVariants) {
-    if (want_tr ? (v.TR != want_tr || v.WR != want_wr) : (v.WR != 1)) continue;
-    const CosSmem L = cos_smem_layout(K, v.TR, v.TJ, v.WR);
-    if (L.total > h->smem_optin) continue;
-    const int JB = 4 * v.TJ;
-    const int nblk = (J + JB - 1) / JB;
-    // padded columns, penalised by smaller row tiles (less reuse of the streamed basis)
-    const long long cost = (long long)nblk * JB * (v.TR == 4 ? 4 : v.TR == 2 ? 5 : 6);
-    if (!best || cost < best_cost || (cost == best_cost && JB > 4 * best->TJ)) {
-      best = &v;
-      best_cost = cost;
-      best_nblk = nblk;
-    }
-  }
-  *nblk_out = best_nblk;
   return best;
 }
 
@@ -102,23 +59,11 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   if (P == 0) return FOP_OK;
   FOP_CUDA(h, cudaSetDevice(h->device));
 
-  const bool fused = getenv("FOP_COS_FUSED") != nullptr;  // A/B knob: single fused kernel
   int nblk = 0;
-  const CosVariant* v = nullptr;
-  const GemmVariant* gv = nullptr;
-  int TJ = 0;
-  if (fused) {
-    v = pick_variant(h, numU, J, &nblk);
-    if (!v) return fail(h, FOP_UNSUPPORTED, "numU=%d does not fit in shared memory", numU);
-    TJ = v->TJ;
-  } else {
-    gv = pick_gemm(J, &nblk);
-    TJ = gv->TJ;
-  }
-  const int JB = 4 * TJ, Jp = nblk * JB;
+  const GemmVariant* gv = pick_gemm(J, &nblk);
+  const int JB = 8 * gv->NB, Jp = nblk * JB;
   // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
-  const int KK = fused ? 2 * numU : ((2 * numU + DM_KC - 1) / DM_KC) * DM_KC;
-  const bool use_dfma = getenv("FOP_COS_GEMM") && std::string(getenv("FOP_COS_GEMM")) == "dfma";
+  const int KK = ((2 * numU + DM_KC - 1) / DM_KC) * DM_KC;
 
   // Strike-grid tables (u_k, V_k, strikes, maturities, cos/sin basis): rebuilt only when
   // (K_desc, S0, T, numU) change -- a calibration loop keeps them fixed while theta varies.
@@ -174,16 +119,16 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   // Parameter sets are processed in chunks: bounds the coefficient matrix C (4 KiB per row at
   // numU = 256) and the staging of a host-bound price matrix to ~1 GiB each.
   long long chunkP = P;
-  if (!fused) chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * KK * 8)));
+  chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * KK * 8)));
   if (out_host) chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * J * 8)));
   const long long chunk_rows = chunkP * M;
-  const int lossblk = fused ? 1 : nblk;
+  const int lossblk = nblk;
 
   Arena ar(h);
   size_t need = stage_bytes(params, (size_t)P * np * 8);
   if (mkt) need += stage_bytes(mkt, (size_t)M * J * 8);
   if (w) need += stage_bytes(w, (size_t)M * J * 8);
-  if (!fused) need += Arena::pad((size_t)chunk_rows * KK * 8);
+  need += Arena::pad((size_t)chunk_rows * KK * 8);
   if (out_host) need += Arena::pad((size_t)chunk_rows * J * 8);
   if (loss) need += Arena::pad((size_t)P * M * lossblk * 8) + (loss_host ? Arena::pad((size_t)P * 8) : 0);
   FOP_TRY(ar.reserve(need));
@@ -192,45 +137,19 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
   if (mkt) FOP_TRY(stage_in(h, ar, mkt, (size_t)M * J, &d_mkt));
   if (w) FOP_TRY(stage_in(h, ar, w, (size_t)M * J, &d_w));
-  double* d_C = fused ? nullptr : ar.alloc<double>((size_t)chunk_rows * KK);
+  double* d_C = ar.alloc<double>((size_t)chunk_rows * KK);
   double* d_out_tmp = out_host ? ar.alloc<double>((size_t)chunk_rows * J) : nullptr;
   double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M * lossblk) : nullptr;
   double* d_loss = loss ? (loss_host ? ar.alloc<double>(P) : loss) : nullptr;
 
-  CosSmem L{};
-  size_t gemm_smem = 0;
-  if (fused) {
-    L = cos_smem_layout(numU, v->TR, v->TJ, v->WR);
-    FOP_CUDA(h, cudaFuncSetAttribute(v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  } else {
-    gemm_smem = use_dfma ? cos_gemm_smem(TJ) : cos_dmma_smem(TJ / 2);
-    FOP_CUDA(h, cudaFuncSetAttribute(use_dfma ? gv->kernel : gv->dmma,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
-  }
+  const size_t gemm_smem = cos_dmma_smem(gv->NB);
+  FOP_CUDA(h, cudaFuncSetAttribute(gv->dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
 
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
     const int pc = (int)std::min<long long>(chunkP, P - p0);
     const long long rows = (long long)pc * M;
     double* out_here = out ? (out_host ? d_out_tmp : out + (size_t)p0 * M * J) : nullptr;
-    if (fused) {
-      CosArgs a;
-      a.base = model.base;  a.tc = model.time_change;  a.greek = kind >> 1;  a.kind = kind;
-      a.P = pc;  a.M = M;  a.J = J;  a.K = numU;  a.Jp = Jp;  a.nblk = nblk;  a.np = np;
-      a.r = r;  a.S0 = S0;
-      a.params = d_params + (size_t)p0 * np;
-      a.T = d_T;  a.uk = d_tab;  a.vk = d_tab + numU;  a.basis = d_basis;  a.strikes = d_K;
-      a.out = out_here;
-      a.mkt = d_mkt;  a.w = d_w;
-      a.rowloss = loss ? d_rowloss + (size_t)p0 * M : nullptr;
-      const int R = cos_rows(v->TR, v->WR);
-      const long long ntiles = (rows + R - 1) / R;
-      const int grid = (int)std::min<long long>(ntiles, h->sm_count);
-      {
-        ProfScope ps(h, "cos_fused_kernel");
-        v->kernel<<<grid, 256 * v->WR, L.total, h->stream>>>(a);
-      }
-      FOP_LAUNCH_CHECK(h);
-    } else {
+    {
       CosCoeffArgs ca;
       ca.base = model.base;  ca.tc = model.time_change;  ca.greek = kind >> 1;
       ca.P = pc;  ca.M = M;  ca.K = numU;  ca.Kp = KK / 2;  ca.np = np;
@@ -253,11 +172,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ga.C = d_C;  ga.basis = d_basis;  ga.T = d_T;  ga.strikes = d_K;
       ga.out = out_here;  ga.mkt = d_mkt;  ga.w = d_w;
       ga.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
-      const dim3 ggrid((unsigned)((rows + GEMM_RT - 1) / GEMM_RT), (unsigned)nblk);
+      const dim3 ggrid((unsigned)((rows + DM_RT - 1) / DM_RT), (unsigned)nblk);
       {
         ProfScope ps(h, "cos_gemm_kernel");
-        if (use_dfma) gv->kernel<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
-        else gv->dmma<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
+        gv->dmma<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
       }
       FOP_LAUNCH_CHECK(h);
     }

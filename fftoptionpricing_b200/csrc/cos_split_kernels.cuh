@@ -5,11 +5,11 @@
 //                         times V_k cp -> COS coefficients C[row][2k], C[row][2k+1]
 //                         (row = set * M + maturity).  Register-light => high occupancy, which is
 //                         what the long dependent fp64 chains of exp/log/sincos/atan2 need.
-//   2. cos_gemm_kernel    val[row][j] = sum_kk C[row][kk] Bas[kk][j]: tall-skinny real fp64 GEMM
-//                         (A = C streamed from L2/HBM, B = basis shared by every row), 128 x JB
-//                         CTA tiles, 4 x TJ register tiles, cp.async double buffering, then the
-//                         put/call-parity / Greek epilogue and the optional fused squared-error
-//                         row loss.
+//   2. cos_gemm_dmma_kernel  val[row][j] = sum_kk C[row][kk] Bas[kk][j]: tall-skinny real fp64
+//                         GEMM (A = C streamed from L2/HBM, B = basis shared by every row) on the
+//                         fp64 tensor cores, 128 x (8 NB) CTA tiles, cp.async double buffering,
+//                         then the put/call-parity / Greek epilogue and the optional fused
+//                         squared-error row loss.
 // C makes one round trip through L2/HBM (4 KiB per row at numU = 256): at the fp64 rate this is
 // ~20 % of HBM bandwidth and fully hidden; in exchange each kernel runs at the occupancy / tile
 // shape that suits it (the single fused kernel in cos_kernels.cuh sat at 33 % fp64-pipe
@@ -103,137 +103,11 @@ struct CosGemmArgs {
   double* rowloss;        // [rows][nblk] or nullptr
 };
 
-constexpr int GEMM_KC = 32;           // kk per stage
-constexpr int GEMM_RT = 128;          // rows per CTA
-constexpr int GEMM_AS = GEMM_KC + 2;  // row stride of the A tile in doubles (272 B)
-
-__host__ __device__ inline size_t cos_gemm_smem(int TJ) {
-  const int JB = 4 * TJ;
-  const size_t stage = (size_t)GEMM_RT * GEMM_AS * 8 + (size_t)GEMM_KC * JB * 8;
-  const size_t epi = (size_t)GEMM_RT * (JB + 2) * 8;
-  const size_t main = 2 * stage;
-  return main > epi ? main : epi;
-}
-
-template <int TJ>
-__global__ void __launch_bounds__(128, 2) cos_gemm_kernel(const CosGemmArgs a) {
-  constexpr int TR = 4;
-  constexpr int JB = 4 * TJ, JBP = JB + 2, TJH = TJ / 2;
-  constexpr int NT = 128;
-  constexpr size_t A_BYTES = (size_t)GEMM_RT * GEMM_AS * 8;
-  constexpr size_t STAGE = A_BYTES + (size_t)GEMM_KC * JB * 8;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, cg = lane & 3;
-  const long long row0 = (long long)blockIdx.x * GEMM_RT;
-  const int blk = blockIdx.y;
-  const int nrows = (int)min((long long)GEMM_RT, a.rows - row0);
-  const int KK = a.KK;
-  const int nchunks = (KK + GEMM_KC - 1) / GEMM_KC;
-
-  auto issue = [&](int c, int buf) {
-    double* As = reinterpret_cast<double*>(smem_raw + (size_t)buf * STAGE);
-    double* Bs = reinterpret_cast<double*>(smem_raw + (size_t)buf * STAGE + A_BYTES);
-    const int kk0 = c * GEMM_KC;
-    const int nk = min(GEMM_KC, KK - kk0);  // even (KK is even, GEMM_KC is even)
-    const int apieces = nk / 2;             // 16-byte pieces per row
-    for (int q = tid; q < GEMM_RT * apieces; q += NT) {
-      const int rr = q / apieces, pc = q - rr * apieces;
-      const int rsrc = rr < nrows ? rr : nrows - 1;  // clamp: rows past the end are never stored
-      cp_async16(As + rr * GEMM_AS + 2 * pc, a.C + (size_t)(row0 + rsrc) * KK + kk0 + 2 * pc);
-    }
-    constexpr int CPR = JB / 2;
-    for (int q = tid; q < nk * CPR; q += NT) {
-      const int rr = q / CPR, cc = q - rr * CPR;
-      cp_async16(Bs + rr * JB + 2 * cc, a.basis + (size_t)(kk0 + rr) * a.Jp + (size_t)blk * JB + 2 * cc);
-    }
-    cp_async_commit();
-  };
-
-  double acc[TR][TJ];
-#pragma unroll
-  for (int i = 0; i < TR; ++i)
-#pragma unroll
-    for (int j = 0; j < TJ; ++j) acc[i][j] = 0.0;
-
-  // thread rows: warp*32 + 8 t + g  (8 consecutive rows per LDS -> conflict-free at stride 272 B)
-  const int arow = warp * 32 + g;
-  issue(0, 0);
-  for (int c = 0; c < nchunks; ++c) {
-    const int buf = c & 1;
-    if (c + 1 < nchunks) {
-      issue(c + 1, buf ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const double* As = reinterpret_cast<const double*>(smem_raw + (size_t)buf * STAGE);
-    const double* Bs = reinterpret_cast<const double*>(smem_raw + (size_t)buf * STAGE + A_BYTES);
-    const int nk = min(GEMM_KC, KK - c * GEMM_KC);
-#pragma unroll 2
-    for (int kc = 0; kc < nk; kc += 2) {
-      double2 av[TR];
-#pragma unroll
-      for (int t = 0; t < TR; ++t)
-        av[t] = *reinterpret_cast<const double2*>(As + (arow + 8 * t) * GEMM_AS + kc);
-      const double* bp = Bs + kc * JB + 2 * cg;
-#pragma unroll
-      for (int h = 0; h < TJH; ++h) {
-        const double2 b0 = *reinterpret_cast<const double2*>(bp + 8 * h);
-        const double2 b1 = *reinterpret_cast<const double2*>(bp + JB + 8 * h);
-#pragma unroll
-        for (int t = 0; t < TR; ++t) {
-          acc[t][2 * h] = fma(av[t].x, b0.x, acc[t][2 * h]);
-          acc[t][2 * h + 1] = fma(av[t].x, b0.y, acc[t][2 * h + 1]);
-          acc[t][2 * h] = fma(av[t].y, b1.x, acc[t][2 * h]);
-          acc[t][2 * h + 1] = fma(av[t].y, b1.y, acc[t][2 * h + 1]);
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- epilogue through shared memory: one warp per row, lanes along strikes
-  double* Es = reinterpret_cast<double*>(smem_raw);
-#pragma unroll
-  for (int t = 0; t < TR; ++t)
-#pragma unroll
-    for (int h = 0; h < TJH; ++h)
-      *reinterpret_cast<double2*>(Es + (size_t)(arow + 8 * t) * JBP + 2 * cg + 8 * h) =
-          make_double2(acc[t][2 * h], acc[t][2 * h + 1]);
-  __syncthreads();
-  for (int rr = warp; rr < nrows; rr += NT / 32) {
-    const long long row = row0 + rr;
-    const int m = (int)(row % a.M);
-    const double disc = exp(-a.r * __ldg(a.T + m));
-    double lsum = 0.0;
-    for (int jj = lane; jj < JB; jj += 32) {
-      const int j = blk * JB + jj;
-      if (j < a.J) {
-        const double o = cos_epilogue(a.kind, Es[(size_t)rr * JBP + jj], disc, __ldg(a.strikes + j),
-                                      a.S0, a.r);
-        if (a.out) a.out[(size_t)row * a.J + j] = o;
-        if (a.mkt) {
-          const double d = o - __ldg(a.mkt + (size_t)m * a.J + j);
-          lsum += (a.w ? __ldg(a.w + (size_t)m * a.J + j) : 1.0) * d * d;
-        }
-      }
-    }
-    if (a.rowloss) {
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
-      if (lane == 0) a.rowloss[(size_t)row * a.nblk + blk] = lsum;
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // fp64 tensor-core contraction (mma.sync.m8n8k4.f64, "DMMA").
 //
-// Why: ncu on the DFMA kernel above (profiles/r1_cos_c5_split_v1_ncu.json) shows it is
-// shared-memory bound -- every LDS.128 costs 4 wavefronts whether or not lanes broadcast, a
+// Why: ncu on the first, DFMA register-tiled version of this kernel
+// (profiles/r1_cos_c5_split_v1_ncu.json) showed it to be shared-memory bound -- every LDS.128 costs 4 wavefronts whether or not lanes broadcast, a
 // 4 x 18 register tile needs 22 x 16 B per lane per 144 FMAs = 1.22x the 128 B/clk the LSU can
 // deliver at the fp64 rate, and a tile large enough (8 x 18) does not fit in 255 registers.  The
 // MMA unit shares the A / B fragments across lanes in hardware: a 32 x 72 warp tile needs
