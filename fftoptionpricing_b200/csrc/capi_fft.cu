@@ -38,7 +38,8 @@ inline int get_twiddles(fop_handle_t h, int N, const double2** out) { return fop
 
 // ---- generic load / store functors (fop_fft)
 struct LoadGen {
-  static constexpr size_t aux_bytes = 0;
+  static constexpr bool has_cf = false;
+  static size_t aux_bytes(int) { return 0; }
   const cd* data;
   int N;
   __device__ void prepare(void*, int, int) const {}
@@ -69,8 +70,9 @@ __global__ void tiny_dft_kernel(cd* data, int batch, int N, int sign) {
 
 // ---- Carr-Madan functors (OptionPricing.h:564-567 CallAug, :582-607 CarrMadanGeneric)
 struct CmGen {
-  static constexpr int MAX_SETS = 256;  // >= transforms per CTA of the single-CTA engine
-  static constexpr size_t aux_bytes = sizeof(ModelConsts) * MAX_SETS;
+  static constexpr bool has_cf = true;
+  // per-set constants of the transforms a CTA works on at a time
+  static size_t aux_bytes(int sets_per_cta) { return sizeof(ModelConsts) * (size_t)sets_per_cta; }
   int base, tc, np;
   const double* params;
   double r, T, ada, alpha, discount, b;
@@ -105,8 +107,8 @@ struct CmEpi {
   // call_m = S0 Re(X_m) e^{-alpha(-b + lambda m)} ada/(3 pi)  (:605);  put by parity (:652)
   __device__ void operator()(int p, int k, cd X) const {
     const double kk = -b + lambda * k;
-    double v = S0 * X.x * exp(-alpha * kk) * ada / (M_PI * 3.0);
-    if (is_put) v = v - S0 + S0 * exp(kk) * discount;
+    double v = S0 * X.x * fm_exp(-alpha * kk) * ada / (M_PI * 3.0);
+    if (is_put) v = v - S0 + S0 * fm_exp(kk) * discount;
     out[(size_t)p * N + k] = v;
   }
 };
@@ -118,14 +120,14 @@ int run_fft(fop_handle_t h, Arena& ar, int N, int batch, Gen gen, Epi epi) {
   if (n <= 13) {
     const double2* tw = nullptr;
     FOP_TRY(get_twiddles(h, N, &tw));
-    const size_t smem = fft_single_smem(n) + Gen::aux_bytes;
+    const size_t smem = fft_single_smem(n) + Gen::aux_bytes(fft_single_tpb(n));
     auto kern = fft_single_kernel<SIGN, Gen, Epi>;
     FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tpb = fft_single_tpb(n);
     const int groups = (batch + tpb - 1) / tpb;
     const int grid = std::min(groups, h->sm_count * 8);
     {
-      ProfScope ps(h, Gen::aux_bytes ? "carr_madan_single_kernel" : "fft_single_kernel");
+      ProfScope ps(h, Gen::has_cf ? "carr_madan_single_kernel" : "fft_single_kernel");
       kern<<<grid, fft_single_threads(n), smem, h->stream>>>(n, batch, tw, gen, epi);
     }
     FOP_LAUNCH_CHECK(h);
@@ -143,18 +145,18 @@ int run_fft(fop_handle_t h, Arena& ar, int N, int batch, Gen gen, Epi epi) {
   if (!scratch) return fail(h, FOP_OOM, "arena exhausted for four-step scratch");
   auto ka = fft_cols_kernel<SIGN, Gen>;
   auto kb = fft_rows_kernel<SIGN, Epi>;
-  const size_t sa = four_step_smem(f.n1, f.ta) + Gen::aux_bytes, sb = four_step_smem(f.n2, f.tb);
+  const size_t sa = four_step_smem(f.n1, f.ta) + Gen::aux_bytes(1), sb = four_step_smem(f.n2, f.tb);
   FOP_CUDA(h, cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa));
   FOP_CUDA(h, cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
   for (int p0 = 0; p0 < batch; p0 += pb) {
     const int pc = std::min(pb, batch - p0);
     {
-      ProfScope ps(h, Gen::aux_bytes ? "carr_madan_cols_kernel" : "fft_cols_kernel");
+      ProfScope ps(h, Gen::has_cf ? "carr_madan_cols_kernel" : "fft_cols_kernel");
       ka<<<dim3(N2 / f.ta, pc), f.ta * (N1 / 16), sa, h->stream>>>(f, p0, tw1, twN, gen, scratch);
     }
     FOP_LAUNCH_CHECK(h);
     {
-      ProfScope ps(h, Gen::aux_bytes ? "carr_madan_rows_kernel" : "fft_rows_kernel");
+      ProfScope ps(h, Gen::has_cf ? "carr_madan_rows_kernel" : "fft_rows_kernel");
       kb<<<dim3(N1 / f.tb, pc), f.tb * (N2 / 16), sb, h->stream>>>(f, p0, tw2, scratch, epi);
     }
     FOP_LAUNCH_CHECK(h);

@@ -58,10 +58,17 @@ __global__ void __launch_bounds__(512) fft_single_kernel(int n, int batch, const
     __syncthreads();
     gen.prepare(aux, p0, cnt);  // block-wide hook (per-set constants into aux shared memory)
     // cooperative generation, natural order (consecutive threads -> consecutive j)
+    // two independent elements per trip: the (straight-line) generator code interleaves
 #pragma unroll 1
-    for (int idx = threadIdx.x; idx < cnt * N; idx += blockDim.x) {
-      const int sl = idx >> n, j = idx & (N - 1);
-      sm0[(size_t)sl * psz + fft_pad(j)] = gen(aux, p0, p0 + sl, j);
+    for (int idx = threadIdx.x; idx < cnt * N; idx += 2 * blockDim.x) {
+      const int idx1 = idx + blockDim.x;
+      const bool has1 = idx1 < cnt * N;
+      const int i1 = has1 ? idx1 : idx;
+      const int sl0 = idx >> n, j0 = idx & (N - 1), sl1 = i1 >> n, j1 = i1 & (N - 1);
+      const cd v0 = gen(aux, p0, p0 + sl0, j0);
+      const cd v1 = gen(aux, p0, p0 + sl1, j1);
+      sm0[(size_t)sl0 * psz + fft_pad(j0)] = v0;
+      if (has1) sm0[(size_t)sl1 * psz + fft_pad(j1)] = v1;
     }
     __syncthreads();
     for (int ps = 0; ps < np; ++ps) {
@@ -108,10 +115,15 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(FourStep f, int p_base, c
   cd* smA = reinterpret_cast<cd*>(fft_smem_raw);
   void* aux = fft_smem_raw + (size_t)f.ta * psz * sizeof(cd);
   gen.prepare(aux, p, 1);
+  // two independent elements per trip (N1 * ta is a multiple of 2 * blockDim)
 #pragma unroll 1
-  for (int idx = threadIdx.x; idx < N1 * f.ta; idx += blockDim.x) {
-    const int cc = idx % f.ta, j1 = idx / f.ta;
-    smA[(size_t)cc * psz + fft_pad(j1)] = gen(aux, p, p, j1 * N2 + blockIdx.x * f.ta + cc);
+  for (int idx = threadIdx.x; idx < N1 * f.ta; idx += 2 * blockDim.x) {
+    const int idx1 = idx + blockDim.x;
+    const int c0 = idx % f.ta, r0 = idx / f.ta, c1 = idx1 % f.ta, r1 = idx1 / f.ta;
+    const cd v0 = gen(aux, p, p, r0 * N2 + blockIdx.x * f.ta + c0);
+    const cd v1 = gen(aux, p, p, r1 * N2 + blockIdx.x * f.ta + c1);
+    smA[(size_t)c0 * psz + fft_pad(r0)] = v0;
+    smA[(size_t)c1 * psz + fft_pad(r1)] = v1;
   }
   __syncthreads();
   for (int ps = 0; ps < np; ++ps) {

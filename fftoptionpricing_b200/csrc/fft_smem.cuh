@@ -290,7 +290,9 @@ FOP_HD void fft_dif_pass(cd* sm, int b, int n, int p, const double2* __restrict_
     const int S = N >> (4 * (p + 1));
     const int base = fft_base16(b, S), q = b % S;
     load16(sm, base, S, x);
-    dif16_regs<SIGN>(x, q, N / (S << 4), tw);
+    // one exact table twiddle W_L^q per thread, its 15 powers by multiplication (depth 4)
+    if (S > 1) dif16_regs_pow<SIGN>(x, tw_load<SIGN>(tw, q * (N / (S << 4))));
+    else Dft<16, SIGN>::run(x);
     store16_dft<SIGN>(sm, base, S, x);
   } else {
     load16(sm, 16 * b, 1, x);
@@ -319,7 +321,8 @@ FOP_HD void fft_dit_pass(cd* sm, int b, int n, int p, const double2* __restrict_
   const int S = (rl == 16 ? 1 : rl) << (4 * p16);
   const int base = fft_base16(b, S), q = b % S;
   load16(sm, base, S, x);
-  dit16_regs<SIGN>(x, q, N / (S << 4), tw);
+  if (S > 1) dit16_regs_pow<SIGN>(x, tw_load<SIGN>(tw, q * (N / (S << 4))));
+  else Dft<16, SIGN>::run(x);
   store16_dft<SIGN>(sm, base, S, x);
 }
 
