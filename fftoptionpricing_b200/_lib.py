@@ -43,6 +43,9 @@ _SIGNATURES = {
     "fop_cos": (C.c_int, [C.c_void_p, fop_model_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                           C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_int,
                           C.c_void_p]),
+    "fop_cos_greeks": (C.c_int, [C.c_void_p, fop_model_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int,
+                                 C.POINTER(C.c_int), C.c_int, C.c_void_p]),
     "fop_fsts": (C.c_int, [C.c_void_p, fop_model_t, C.c_void_p, C.c_int, C.c_int, C.c_double,
                            C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                            C.c_void_p]),

@@ -45,16 +45,24 @@ double vk_put(double xMin, double u, int k) {
   return phi - chi;
 }
 
+// kinds[nk]: output kinds (fop_cos_kind); out = [nk][P][M][J] (or nullptr in loss-only mode)
 int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, const double* K_desc,
-            int J, double S0, double r, const double* T, int M, int numU, int kind,
+            int J, double S0, double r, const double* T, int M, int numU, const int* kinds, int nk,
             const double* mkt, const double* w, double* out, double* loss) {
   if (!h) return FOP_INVALID_ARG;
   const int np = num_params(model.base, model.time_change);
   if (np == 0) return fail(h, FOP_INVALID_ARG, "unknown model (%d,%d)", model.base, model.time_change);
   if (!params || !K_desc || !T) return fail(h, FOP_INVALID_ARG, "null input pointer");
   if (!out && !loss) return fail(h, FOP_INVALID_ARG, "no output requested");
-  if (P < 0 || J < 2 || M < 1 || numU < 1 || numU > 1024 || kind < 0 || kind > 7)
-    return fail(h, FOP_INVALID_ARG, "bad sizes P=%d J=%d M=%d numU=%d kind=%d", P, J, M, numU, kind);
+  if (P < 0 || J < 2 || M < 1 || numU < 1 || numU > 1024 || !kinds || nk < 1 || nk > 8)
+    return fail(h, FOP_INVALID_ARG, "bad sizes P=%d J=%d M=%d numU=%d nkinds=%d", P, J, M, numU, nk);
+  int greek_mask = 0, plane_of[4] = {0, 0, 0, 0}, ngreeks = 0;
+  for (int i = 0; i < nk; ++i) {
+    if (kinds[i] < 0 || kinds[i] > 7) return fail(h, FOP_INVALID_ARG, "unknown output kind %d", kinds[i]);
+    greek_mask |= 1 << (kinds[i] >> 1);
+  }
+  for (int g = 0; g < 4; ++g)
+    if (greek_mask >> g & 1) plane_of[g] = ngreeks++;
   if (loss && !mkt) return fail(h, FOP_INVALID_ARG, "loss requested without market prices");
   if (P == 0) return FOP_OK;
   FOP_CUDA(h, cudaSetDevice(h->device));
@@ -119,7 +127,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   // Parameter sets are processed in chunks: bounds the coefficient matrix C (4 KiB per row at
   // numU = 256) and the staging of a host-bound price matrix to ~1 GiB each.
   long long chunkP = P;
-  chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * KK * 8)));
+  chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * KK * 8 * ngreeks)));
   if (out_host) chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * J * 8)));
   const long long chunk_rows = chunkP * M;
   const int lossblk = nblk;
@@ -128,7 +136,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   size_t need = stage_bytes(params, (size_t)P * np * 8);
   if (mkt) need += stage_bytes(mkt, (size_t)M * J * 8);
   if (w) need += stage_bytes(w, (size_t)M * J * 8);
-  need += Arena::pad((size_t)chunk_rows * KK * 8);
+  need += Arena::pad((size_t)chunk_rows * KK * 8 * ngreeks);
   if (out_host) need += Arena::pad((size_t)chunk_rows * J * 8);
   if (loss) need += Arena::pad((size_t)P * M * lossblk * 8) + (loss_host ? Arena::pad((size_t)P * 8) : 0);
   FOP_TRY(ar.reserve(need));
@@ -137,7 +145,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
   if (mkt) FOP_TRY(stage_in(h, ar, mkt, (size_t)M * J, &d_mkt));
   if (w) FOP_TRY(stage_in(h, ar, w, (size_t)M * J, &d_w));
-  double* d_C = ar.alloc<double>((size_t)chunk_rows * KK);
+  double* d_C = ar.alloc<double>((size_t)chunk_rows * KK * ngreeks);
   double* d_out_tmp = out_host ? ar.alloc<double>((size_t)chunk_rows * J) : nullptr;
   double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M * lossblk) : nullptr;
   double* d_loss = loss ? (loss_host ? ar.alloc<double>(P) : loss) : nullptr;
@@ -148,10 +156,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
     const int pc = (int)std::min<long long>(chunkP, P - p0);
     const long long rows = (long long)pc * M;
-    double* out_here = out ? (out_host ? d_out_tmp : out + (size_t)p0 * M * J) : nullptr;
     {
       CosCoeffArgs ca;
-      ca.base = model.base;  ca.tc = model.time_change;  ca.greek = kind >> 1;
+      ca.base = model.base;  ca.tc = model.time_change;
+      ca.greek_mask = greek_mask;  ca.plane = (size_t)rows * KK;
       ca.P = pc;  ca.M = M;  ca.K = numU;  ca.Kp = KK / 2;  ca.np = np;
       ca.spb = std::max(1, std::min(COEFF_MAX_SPB, 1024 / ca.Kp));
       ca.r = r;
@@ -166,11 +174,17 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
         else cos_coeff_kernel<1><<<cgrid, 256, 0, h->stream>>>(ca);
       }
       FOP_LAUNCH_CHECK(h);
+    }
+    for (int ik = 0; ik < nk; ++ik) {
+      const int kind = kinds[ik];
+      double* out_k = out ? out + (size_t)ik * P * M * J + (size_t)p0 * M * J : nullptr;
       CosGemmArgs ga;
       ga.kind = kind;  ga.M = M;  ga.J = J;  ga.KK = KK;  ga.Jp = Jp;  ga.nblk = nblk;
       ga.rows = rows;  ga.r = r;  ga.S0 = S0;
-      ga.C = d_C;  ga.basis = d_basis;  ga.T = d_T;  ga.strikes = d_K;
-      ga.out = out_here;  ga.mkt = d_mkt;  ga.w = d_w;
+      ga.C = d_C + (size_t)plane_of[kind >> 1] * rows * KK;
+      ga.basis = d_basis;  ga.T = d_T;  ga.strikes = d_K;
+      ga.out = out ? (out_host ? d_out_tmp : out_k) : nullptr;
+      ga.mkt = d_mkt;  ga.w = d_w;
       ga.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
       const dim3 ggrid((unsigned)((rows + DM_RT - 1) / DM_RT), (unsigned)nblk);
       {
@@ -178,10 +192,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
         gv->dmma<<<ggrid, 128, gemm_smem, h->stream>>>(ga);
       }
       FOP_LAUNCH_CHECK(h);
+      if (out_host)
+        FOP_CUDA(h, cudaMemcpyAsync(out_k, d_out_tmp, (size_t)rows * J * 8, cudaMemcpyDeviceToHost,
+                                    h->stream));
     }
-    if (out_host)
-      FOP_CUDA(h, cudaMemcpyAsync(out + (size_t)p0 * M * J, d_out_tmp, (size_t)rows * J * 8,
-                                  cudaMemcpyDeviceToHost, h->stream));
   }
   if (loss) {
     {
@@ -203,16 +217,25 @@ extern "C" {
 int fop_cos(fop_handle_t h, fop_model_t model, const double* params, int P, const double* K_desc,
             int J, double S0, double r, const double* T, int M, int numU, int kind, double* out) {
   if (h && !out) return fop::fail(h, FOP_INVALID_ARG, "null output pointer");
-  return cos_run(h, model, params, P, K_desc, J, S0, r, T, M, numU, kind, nullptr, nullptr, out,
+  return cos_run(h, model, params, P, K_desc, J, S0, r, T, M, numU, &kind, 1, nullptr, nullptr, out,
                  nullptr);
+}
+
+int fop_cos_greeks(fop_handle_t h, fop_model_t model, const double* params, int P,
+                   const double* K_desc, int J, double S0, double r, const double* T, int M,
+                   int numU, const int* kinds, int nkinds, double* out) {
+  if (h && !out) return fop::fail(h, FOP_INVALID_ARG, "null output pointer");
+  return cos_run(h, model, params, P, K_desc, J, S0, r, T, M, numU, kinds, nkinds, nullptr, nullptr,
+                 out, nullptr);
 }
 
 int fop_cos_loss(fop_handle_t h, fop_model_t model, const double* params, int P,
                  const double* K_desc, int J, double S0, double r, const double* T, int M,
                  int numU, const double* mkt, const double* w, double* loss, double* prices_out) {
   if (h && (!loss || !mkt)) return fop::fail(h, FOP_INVALID_ARG, "null loss / market pointer");
-  return cos_run(h, model, params, P, K_desc, J, S0, r, T, M, numU, FOP_CALL_PRICE, mkt, w,
-                 prices_out, loss);
+  const int kind = FOP_CALL_PRICE;
+  return cos_run(h, model, params, P, K_desc, J, S0, r, T, M, numU, &kind, 1, mkt, w, prices_out,
+                 loss);
 }
 
 }  // extern "C"

@@ -20,14 +20,16 @@
 namespace fop {
 
 struct CosCoeffArgs {
-  int base, tc, greek;
+  int base, tc;
+  int greek_mask;      // bit g set: emit the coefficients of transform g (0 price 1 delta 2 gamma 3 theta)
+  size_t plane;        // doubles between the coefficient matrices of consecutive emitted transforms
   int P, M, K, Kp, np, spb;  // Kp = padded u count (row stride of C = 2 Kp); spb = sets per block
   double r;
   const double* params;  // [P][np]
   const double* T;       // [M]
   const double* uk;      // [K]
   const double* vk;      // [K]
-  double* C;             // [P*M][2K]
+  double* C;             // [n_greeks][P*M][2 Kp]
 };
 
 constexpr int COEFF_MAX_SPB = 64;
@@ -42,15 +44,30 @@ __device__ __forceinline__ void coeff_maturities(const CosCoeffArgs& a, const Mo
   for (; m + ILP <= M; m += ILP) {
     cd d[ILP];
 #pragma unroll
-    for (int i = 0; i < ILP; ++i) d[i] = cf_log_at_mode<MODE>(mc, pre, __ldg(a.T + m + i));
+    for (int i = 0; i < ILP; ++i) d[i] = cexp(cf_log_at_mode<MODE>(mc, pre, __ldg(a.T + m + i)));
+    // one CF evaluation feeds every requested transform (price / delta / gamma / theta)
+    double2* cg = crow;
 #pragma unroll
-    for (int i = 0; i < ILP; ++i) d[i] = option_transform(a.greek, cexp(d[i]), u, a.r);
+    for (int g = 0; g < 4; ++g) {
+      if (!(a.greek_mask >> g & 1)) continue;
 #pragma unroll
-    for (int i = 0; i < ILP; ++i) crow[(size_t)(m + i) * Kp] = make_double2(d[i].x * v, d[i].y * v);
+      for (int i = 0; i < ILP; ++i) {
+        const cd t = option_transform(g, d[i], u, a.r);
+        cg[(size_t)(m + i) * Kp] = make_double2(t.x * v, t.y * v);
+      }
+      cg += a.plane / 2;
+    }
   }
   for (; m < M; ++m) {
-    const cd d = option_transform(a.greek, cexp(cf_log_at_mode<MODE>(mc, pre, __ldg(a.T + m))), u, a.r);
-    crow[(size_t)m * Kp] = make_double2(d.x * v, d.y * v);
+    const cd phi = cexp(cf_log_at_mode<MODE>(mc, pre, __ldg(a.T + m)));
+    double2* cg = crow;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (!(a.greek_mask >> g & 1)) continue;
+      const cd t = option_transform(g, phi, u, a.r);
+      cg[(size_t)m * Kp] = make_double2(t.x * v, t.y * v);
+      cg += a.plane / 2;
+    }
   }
 }
 
@@ -71,7 +88,12 @@ __global__ void __launch_bounds__(256) cos_coeff_kernel(const CosCoeffArgs a) {
       const int s = idx / Kp, k = idx - s * Kp;
       double2* crow = reinterpret_cast<double2*>(a.C) + (size_t)(p0 + s) * M * Kp + k;
       if (k >= K) {  // zero padding so the contraction can run full stages
-        for (int m = 0; m < M; ++m) crow[(size_t)m * Kp] = make_double2(0.0, 0.0);
+        double2* cg = crow;
+        for (int g = 0; g < 4; ++g) {
+          if (!(a.greek_mask >> g & 1)) continue;
+          for (int m = 0; m < M; ++m) cg[(size_t)m * Kp] = make_double2(0.0, 0.0);
+          cg += a.plane / 2;
+        }
         continue;
       }
       const ModelConsts& mc = consts[s];

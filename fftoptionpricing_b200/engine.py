@@ -167,6 +167,19 @@ class Engine:
                                     ob.ptr))
         return out
 
+    def cos_greeks(self, base, tc, params, K_desc, S0, r, T: Sequence[float], numU, kinds, out=None):
+        """Several output kinds (price / delta / gamma / theta, call or put) from one pass over
+        the characteristic function.  Returns [len(kinds)][P][M][J]."""
+        pb, P = self._params(base, tc, params)
+        Kb = _Buf(K_desc)
+        Tb = _Buf(T if _is_torch(T) else np.atleast_1d(np.asarray(T, dtype=np.float64)))
+        kk = (C.c_int * len(kinds))(*[int(k) for k in kinds])
+        out, ob = self._out(out, (len(kinds), P, Tb.size, Kb.size))
+        self._check(self._L.fop_cos_greeks(self._h, _lib.fop_model_t(base, tc), pb.ptr, P, Kb.ptr,
+                                           Kb.size, float(S0), float(r), Tb.ptr, Tb.size, int(numU),
+                                           kk, len(kinds), ob.ptr))
+        return out
+
     def fsts(self, base, tc, params, N, xmax, strike, r, T, steps=1, american=False, payoff=0,
              kind=0, out=None):
         pb, P = self._params(base, tc, params)

@@ -136,6 +136,16 @@ int fop_cos(fop_handle_t h, fop_model_t model, const double* params, int P,
             const double* K_desc, int J, double S0, double r, const double* T, int M, int numU,
             int kind, double* out);
 
+/* All requested output kinds from ONE pass over the characteristic function (the
+ * reference evaluates the CF again for each of FangOostCallPrice / Delta / Gamma / Theta,
+ * OptionPricing.h:358-559; here price, delta, gamma and theta coefficients come from the same CF
+ * value and share the strike basis).  kinds [nkinds] of enum fop_cos_kind, 1 <= nkinds <= 8;
+ * out [nkinds][P][M][J].
+ */
+int fop_cos_greeks(fop_handle_t h, fop_model_t model, const double* params, int P,
+                   const double* K_desc, int J, double S0, double r, const double* T, int M,
+                   int numU, const int* kinds, int nkinds, double* out);
+
 /* ---- FSTS ------------------------------------------------------------------------------------
  * Replaces optionprice::FSTS{Price,Delta,Gamma,Theta} (OptionPricing.h:185-281) and FSTSGeneric
  * (:155-184): steps = 1, american = 0 is the reference's single FFT -> multiply -> IFFT.

@@ -152,3 +152,20 @@ def test_ragged_tiles_and_many_maturities(engine, best_oracle):
         got = engine.cos(0, 1, prm, K, 100.0, .02, T, numU, 0)
         ref = best_oracle.cos(0, 1, prm, K, 100.0, .02, T, numU, 0)
         assert_parity(got, ref, what=f"ragged P={P} M={M} J={J} numU={numU}")
+
+
+def test_all_greeks_from_one_cf_pass(engine, best_oracle):
+    """fop_cos_greeks: price, delta, gamma, theta for calls and puts out of a single
+    characteristic-function pass must equal the eight separate reference entry points
+    (OptionPricing.h:358-559).  Theta only for a Levy model (OptionPricing.h:66 warns it is wrong
+    under a time change -- it is still what the reference computes, so Heston is compared too)."""
+    for base, tc, prm in [(2, 0, CASES.cgmy_batch(5)), (0, 1, CASES.heston_batch(5))]:
+        K = np.concatenate([[5000.0], np.linspace(180.0, 40.0, 37), [.3]])
+        T = [.25, 1.0, 2.0]
+        kinds = list(range(8))
+        got = engine.cos_greeks(base, tc, prm, K, 100.0, .03, T, 128, kinds)
+        for i, kind in enumerate(kinds):
+            ref = best_oracle.cos(base, tc, prm, K, 100.0, .03, T, 128, kind)
+            assert_parity(got[i], ref, what=f"greeks kind={kind} model=({base},{tc})")
+        sub = engine.cos_greeks(base, tc, prm, K, 100.0, .03, T, 128, [5, 2])
+        assert np.array_equal(sub[0], got[5]) and np.array_equal(sub[1], got[2])
