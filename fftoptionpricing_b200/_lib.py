@@ -54,6 +54,8 @@ _SIGNATURES = {
     "fop_cos_loss": (C.c_int, [C.c_void_p, fop_model_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fop_fo_estimate": (C.c_int, [_dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, C.c_int, _dp, C.c_int, _dp]),
     "fop_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "fop_measure_fp64_peak": (C.c_int, [C.c_void_p, _dp]),
 }

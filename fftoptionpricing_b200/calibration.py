@@ -31,6 +31,30 @@ def getObjFn_arr(phiHat, model: CF, uArray, r: float, T: float, engine: Optional
     return objFn
 
 
+def generateFOEstimate(strikes, options, stock, r, t, minStrike, maxStrike):
+    """Mirror of optioncal::generateFOEstimate (OptionCalibration.h:157-184): returns
+    ``estimate(N, uArray) -> phiHat`` (complex128 [len(uArray)]).  Host computation (spline +
+    Simpson DFT), done once per market snapshot; feed the result to getObjFn_arr."""
+    import ctypes as C
+
+    from . import _lib
+    L = _lib.load_library()
+    k = np.ascontiguousarray(np.asarray(strikes, dtype=np.float64))
+    o = np.ascontiguousarray(np.asarray(options, dtype=np.float64))
+
+    def estimate(N, uArray):
+        u = np.ascontiguousarray(np.asarray(uArray, dtype=np.float64))
+        out = np.empty(2 * u.size)
+        st = L.fop_fo_estimate(k.ctypes.data_as(_lib._dp), o.ctypes.data_as(_lib._dp), k.size,
+                               float(stock), float(r), float(t), float(minStrike), float(maxStrike),
+                               int(N), u.ctypes.data_as(_lib._dp), u.size, out.ctypes.data_as(_lib._dp))
+        if st != 0:
+            raise E.FopError(st, "fop_fo_estimate: invalid arguments")
+        return out.view(np.complex128).copy()
+
+    return estimate
+
+
 def shard_bounds(total: int, rank: int, world: int):
     """Contiguous [lo, hi) slice of `total` parameter sets owned by `rank` (sizes differ by <= 1)."""
     base, rem = divmod(total, world)

@@ -180,6 +180,16 @@ int fop_cos_loss(fop_handle_t h, fop_model_t model, const double* params, int P,
                  int numU, const double* mkt, const double* w, double* loss,
                  double* prices_out);
 
+/* Market quotes -> empirical log-CF estimate (HOST function, no GPU work): replaces
+ * optioncal::generateFOEstimate(strikes, options, stock, r, t, minStrike, maxStrike)(N, uArray)
+ * (OptionCalibration.h:157-184; getOptionSpline :105-156; monotone_spline.h).  strikes / options
+ * [n] ascending strikes and their call prices, u [m]; phiHat_out [m][2] (re, im) is what
+ * fop_objfn_cf takes.
+ */
+int fop_fo_estimate(const double* strikes, const double* options, int n, double stock, double r,
+                    double t, double minStrike, double maxStrike, int N, const double* u, int m,
+                    double* phiHat_out);
+
 /* ---- batched FFT (the replacement for fft.hpp:49-61; exposed for parity tests) ---------------
  * In-place unnormalised transforms of `batch` contiguous length-N complex128 sequences
  * (interleaved re,im -- the layout of the reference's CArray, fft.h:12-13).

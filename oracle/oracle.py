@@ -61,6 +61,7 @@ class Oracle:
         L.ora_cos_loss.argtypes = [i, i, _dp, i, _dp, i, d, d, _dp, i, i, _dp, _dp, _dp, _dp]
         L.ora_fft.argtypes = [_dp, i, i, i]
         L.ora_cf.argtypes = [i, i, _dp, d, d, d, d, _dp, _dp]
+        L.ora_fo_estimate.argtypes = [_dp, _dp, i, d, d, d, d, d, i, _dp, i, _dp]
         L.ora_carr_madan_strikes.argtypes = [i, d, d, _dp]
         L.ora_fang_oost_strikes.argtypes = [d, d, d, i, _dp]
         L.ora_strike_underlying.argtypes = [d, d, d, i, _dp]
@@ -145,6 +146,13 @@ class Oracle:
         self._check(self.lib.ora_cf(base, tc, _ptr(p), r, T, float(np.real(u)),
                                     float(np.imag(u)), _ptr(cf), _ptr(lcf)), "cf")
         return complex(cf[0], cf[1]), complex(lcf[0], lcf[1])
+
+    def fo_estimate(self, strikes, options, stock, r, t, minStrike, maxStrike, N, u):
+        k, o, uu = _arr(strikes), _arr(options), _arr(u)
+        out = np.empty(2 * uu.size)
+        self._check(self.lib.ora_fo_estimate(_ptr(k), _ptr(o), k.size, stock, r, t, minStrike,
+                                             maxStrike, N, _ptr(uu), uu.size, _ptr(out)), "fo_estimate")
+        return out.view(np.complex128).copy()
 
     def carr_madan_strikes(self, N, ada, S0):
         out = np.empty(N)

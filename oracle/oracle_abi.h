@@ -36,6 +36,11 @@ int ora_fft(double* data, int batch, int N, int inverse);
 /* CF value phi(u) and log-CF at u = (u_re, u_im) for one parameter set (unit tests of the CF lib) */
 int ora_cf(int base, int tc, const double* params, double r, double T, double u_re, double u_im,
            double* cf_out2, double* logcf_out2);
+/* optioncal::generateFOEstimate(...)(N, u)  (OptionCalibration.h:157-184); the port flavour does
+ * not restate it and returns 4 -- it is pinned by golden vectors from the reference flavour */
+int ora_fo_estimate(const double* strikes, const double* options, int n, double stock, double r,
+                    double t, double minStrike, double maxStrike, int N, const double* u, int m,
+                    double* phiHat_out);
 int ora_carr_madan_strikes(int N, double ada, double S0, double* K_out);
 int ora_fang_oost_strikes(double xMin, double xMax, double S0, int numX, double* K_out);
 int ora_strike_underlying(double xMin, double xMax, double K, int numX, double* S_out);

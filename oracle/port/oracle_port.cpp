@@ -302,6 +302,9 @@ int ora_cf(int base, int tc, const double* params, double r, double T, double u_
   return 0;
 }
 
+int ora_fo_estimate(const double*, const double*, int, double, double, double, double, double, int,
+                    const double*, int, double*) { return 4; }
+
 // OptionPricing.h:120-138
 int ora_carr_madan_strikes(int N, double ada, double S0, double* K_out) {
   const double b = M_PI / ada, lambda = 2.0 * b / N;

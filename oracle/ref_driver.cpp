@@ -219,6 +219,16 @@ int ora_cf(int base, int tc, const double* params, double r, double T, double u_
   return 0;
 }
 
+int ora_fo_estimate(const double* strikes, const double* options, int n, double stock, double r,
+                    double t, double minStrike, double maxStrike, int N, const double* u, int m,
+                    double* phiHat_out) {
+  const std::vector<double> k(strikes, strikes + n), o(options, options + n), uu(u, u + m);
+  const auto est = optioncal::generateFOEstimate(k, o, stock, r, t, minStrike, maxStrike);
+  const auto ph = est(N, uu);
+  for (int l = 0; l < m; ++l) { phiHat_out[2 * l] = ph[l].real(); phiHat_out[2 * l + 1] = ph[l].imag(); }
+  return 0;
+}
+
 int ora_carr_madan_strikes(int N, double ada, double S0, double* K_out) {
   std::vector<double> k = optionprice::getCarrMadanStrikes(ada, S0, N);
   std::memcpy(K_out, k.data(), sizeof(double) * N);

@@ -169,3 +169,23 @@ def test_all_greeks_from_one_cf_pass(engine, best_oracle):
             assert_parity(got[i], ref, what=f"greeks kind={kind} model=({base},{tc})")
         sub = engine.cos_greeks(base, tc, prm, K, 100.0, .03, T, 128, [5, 2])
         assert np.array_equal(sub[0], got[5]) and np.array_equal(sub[1], got[2])
+
+
+def test_quotes_to_objective_end_to_end(engine):
+    """quotes -> phiHat (fop_fo_estimate, host) -> fop_objfn_cf over a population (GPU): the
+    parameter set that generated the quotes must score far better than random ones
+    (the reference's calibration pipeline, generateCharts.cpp:43-115, minus the optimiser)."""
+    import json
+    import os
+
+    from fftoptionpricing_b200 import calibration, models
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "estimator_v1.json")))
+    c = g["cases"][0]  # Heston market
+    u = np.array(g["u"])
+    ph = calibration.generateFOEstimate(c["strikes"], c["options"], c["stock"], c["r"], c["T"],
+                                        c["minStrike"], c["maxStrike"])(c["N"], u)
+    pop = CASES.heston_batch(4096)          # set 0 = the generating parameters
+    obj = calibration.getObjFn_arr(ph, models.heston(0, 0, 0, 0, 0), u, c["r"], c["T"], engine=engine)
+    loss = obj(pop)
+    assert loss.shape == (4096,) and np.all(np.isfinite(loss))
+    assert loss[0] < 0.01 and loss[0] <= np.percentile(loss, 2)
