@@ -126,13 +126,14 @@ class ClockSampler:
 
 def load_ncu_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu summary (or None)."""
-    path = os.path.join(ROOT, "profiles", "r1_cos_c5_ncu.json")
+    # `ncu --set full` capture of this very command (profiles/README.md), per launch
+    path = os.path.join(ROOT, "profiles", "r1_bench_top_kernels_ncu.json")
     try:
         for k in json.load(open(path)):
             if "cos_gemm_kernel" in k["kernel"]:
                 def mb(s):
                     v, u = s.split()[:2]
-                    return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+                    return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
                 return {"bytes": mb(k["dram__bytes_read.sum"]) + mb(k["dram__bytes_write.sum"]),
                         "rows": k.get("rows")}
     except Exception:
