@@ -130,7 +130,7 @@ def load_ncu_traffic():
     path = os.path.join(ROOT, "profiles", "r1_bench_top_kernels_ncu.json")
     try:
         for k in json.load(open(path)):
-            if "cos_gemm_kernel" in k["kernel"]:
+            if "cos_gemm" in k["kernel"]:
                 def mb(s):
                     v, u = s.split()[:2]
                     return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
