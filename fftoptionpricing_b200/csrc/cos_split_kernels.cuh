@@ -175,8 +175,12 @@ __host__ __device__ inline CosEpi cos_epi_consts(int kind, double S0, double r) 
 
 // C rows are padded to KKp = multiple of DM_KC (zero filled), basis rows likewise, so every
 // stage is full and all loop bounds are compile-time constants.
-template <int NB>
-__global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs a) {
+// MB = m-blocks (of 8 rows) per warp: MB = 4 -> 4 warps x 32 rows (72 accumulators/lane at NB = 9),
+// MB = 2 -> 8 warps x 16 rows (36 accumulators/lane, <= 128 registers -> 16 warps/SM instead of 8,
+// which keeps the DMMA pipe busier across barriers / epilogues at 1.7x the smem traffic per MMA).
+template <int NB, int MB>
+__global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kernel(const CosGemmArgs a) {
+  constexpr int NT = 32 * (DM_RT / (8 * MB));
   constexpr int JB = 8 * NB, JBP = JB + 2, BS = dm_bs(NB);
   constexpr size_t A_BYTES = (size_t)DM_RT * DM_AS * 8;
   constexpr size_t STAGE = A_BYTES + (size_t)DM_KC * BS * 8;
@@ -195,17 +199,19 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs
   const CosEpi epi = cos_epi_consts(a.kind, a.S0, a.r);
 
   // cp.async plan (fully coalesced: consecutive threads copy consecutive 16-byte pieces).
-  //   A: piece q = tid + 128 i  ->  row (tid >> 4) + 8 i, piece tid & 15 of the row's 256 B
-  //   B: piece q = tid + 128 i  ->  basis row q / BPC, piece q % BPC   (offsets precomputed)
-  constexpr int BPC = JB / 2;                      // 16-byte pieces per basis row
-  constexpr int NBI = (DM_KC * BPC + 127) / 128;   // B pieces per thread
+  //   A: piece q = tid + NT i  ->  row (tid >> 4) + (NT/16) i, piece tid & 15 of the row's 256 B
+  //   B: piece q = tid + NT i  ->  basis row q / BPC, piece q % BPC   (offsets precomputed)
+  constexpr int BPC = JB / 2;                          // 16-byte pieces per basis row
+  constexpr int NBI = (DM_KC * BPC + NT - 1) / NT;     // B pieces per thread
+  constexpr int ARS = NT / 16;                         // A rows covered per pass
+  constexpr int API = DM_RT / ARS;                     // A passes
   const bool full = nrows == DM_RT;
   const double* abase = a.C + (size_t)(row0 + (tid >> 4)) * KKp + 2 * (tid & 15);
   double* adst = reinterpret_cast<double*>(smem_raw) + (tid >> 4) * DM_AS + 2 * (tid & 15);
   int bsoff[NBI], bgoff[NBI];
 #pragma unroll
   for (int i = 0; i < NBI; ++i) {
-    const int q = tid + 128 * i;
+    const int q = tid + NT * i;
     const int rr = q / BPC, cc = q - rr * BPC;
     bsoff[i] = q < DM_KC * BPC ? rr * BS + 2 * cc : -1;
     bgoff[i] = rr * a.Jp + 2 * cc;
@@ -217,14 +223,14 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs
     const int kk0 = ch * DM_KC;
     if (full) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        cp_async16(adst + so + (8 * i) * DM_AS, abase + kk0 + (size_t)(8 * i) * KKp);
+      for (int i = 0; i < API; ++i)
+        cp_async16(adst + so + (ARS * i) * DM_AS, abase + kk0 + (size_t)(ARS * i) * KKp);
     } else {  // last row tile: clamp the source row (rows past the end are never stored)
 #pragma unroll 1
-      for (int i = 0; i < 16; ++i) {
-        const int rr = (tid >> 4) + 8 * i;
+      for (int i = 0; i < API; ++i) {
+        const int rr = (tid >> 4) + ARS * i;
         const int rs = rr < nrows ? rr : nrows - 1;
-        cp_async16(adst + so + (8 * i) * DM_AS,
+        cp_async16(adst + so + (ARS * i) * DM_AS,
                    a.C + (size_t)(row0 + rs) * KKp + kk0 + 2 * (tid & 15));
       }
     }
@@ -247,13 +253,13 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs
     s_strike[tid] = j < a.J ? __ldg(a.strikes + j) : 0.0;
   }
 
-  double acc[4][NB][2];
+  double acc[MB][NB][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MB; ++i)
 #pragma unroll
     for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  const int wrow = warp * 32;
+  const int wrow = warp * (8 * MB);
   for (int ch = 0; ch < nchunks; ++ch) {
     const int buf = ch & 1;
     if (ch + 1 < nchunks) {
@@ -267,13 +273,13 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs
     const double* Bs = reinterpret_cast<const double*>(smem_raw + (size_t)buf * STAGE + A_BYTES) + c * BS + g;
 #pragma unroll
     for (int ks = 0; ks < DM_KC; ks += 4) {
-      double af[4], bf[NB];
+      double af[MB], bf[NB];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = As[(8 * i) * DM_AS + ks];
+      for (int i = 0; i < MB; ++i) af[i] = As[(8 * i) * DM_AS + ks];
 #pragma unroll
       for (int j = 0; j < NB; ++j) bf[j] = Bs[ks * BS + 8 * j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < MB; ++i)
 #pragma unroll
         for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs
   // ---- epilogue through shared memory: one warp per row, lanes along strikes
   double* Es = reinterpret_cast<double*>(smem_raw);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < MB; ++i)
 #pragma unroll
     for (int j = 0; j < NB; ++j)
       *reinterpret_cast<double2*>(Es + (size_t)(wrow + 8 * i + g) * JBP + 8 * j + 2 * c) =
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(128, 2) cos_gemm_dmma_kernel(const CosGemmArgs
   __syncthreads();
   const int jvalid = min(JB, a.J - blk * JB);
   constexpr int PASSES = (JB + 31) / 32;
-  for (int rr = warp; rr < nrows; rr += 4) {
+  for (int rr = warp; rr < nrows; rr += NT / 32) {
     const long long row = row0 + rr;
     const double rs = s_rowscale[rr];
     const int m = s_rowm[rr];
