@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfftop_b200.so")
+# FFTOP_B200_LIB: another build of the same library (A/B runs of kernel variants under profiles/)
+LIB_PATH = os.environ.get("FFTOP_B200_LIB") or os.path.join(_HERE, "libfftop_b200.so")
 
 _dp = C.POINTER(C.c_double)
 

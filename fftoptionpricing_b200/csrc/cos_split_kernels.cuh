@@ -72,7 +72,7 @@ __device__ __forceinline__ void coeff_maturities(const CosCoeffArgs& a, const Mo
 }
 
 template <int ILP>
-__global__ void __launch_bounds__(256) cos_coeff_kernel(const CosCoeffArgs a) {
+__global__ void __launch_bounds__(256, 2) cos_coeff_kernel(const CosCoeffArgs a) {
   __shared__ ModelConsts consts[COEFF_MAX_SPB];
   const int tid = threadIdx.x;
   const int K = a.K, M = a.M;

@@ -122,11 +122,11 @@ FM_HD double fm_div(double a, double b) {
 
 FM_HD double fm_exp(double x) {
   const double* K = FM_TAB(fm_k);
-  x = x < -746.0 ? -746.0 : x;  // selects keep NaN
-  x = x > 710.0 ? 710.0 : x;
+  // one magnitude clamp (keeps NaN: the comparison is false) so that k below fits an int
+  x = fabs(x) > 1.0e6 ? copysign(1.0e6, x) : x;
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
   const double t = fm_fma(x, K[0], MAGIC);
-  const int k = fm_lo(t);
+  int k = fm_lo(t);
   const double kd = t - MAGIC;
   double r = fm_fma(kd, K[1], x);   // ln2 hi
   r = fm_fma(kd, K[2], r);   // ln2 lo
@@ -135,7 +135,8 @@ FM_HD double fm_exp(double x) {
 #pragma unroll
   for (int i = 1; i <= 10; ++i) q = fm_fma(q, r, c[i]);
   const double p = fm_fma(r * r, q, r) + 1.0;
-  // scale by 2^k in two normal steps (k in [-1077, 1025])
+  // scale by 2^k in two normal steps; |k| clamped to 1100 -> exact 0 / inf outside the range
+  k = k < -1100 ? -1100 : (k > 1100 ? 1100 : k);
   const int k1 = k >> 1, k2 = k - k1;
   return (p * fm_make((1023 + k1) << 20, 0)) * fm_make((1023 + k2) << 20, 0);
 }
@@ -161,13 +162,14 @@ FM_HD void fm_sincos(double x, double* sn, double* cs) {
   }
   const double s0 = fm_fma(r * z, ps, r);
   const double c0 = fm_fma(z * z, pc, fm_fma(-0.5, z, 1.0));
-  // quadrant: q&1 swaps, (q&2) negates sin, ((q+1)&2) negates cos
+  // quadrant: q&1 swaps, (q&2) negates sin, ((q+1)&2) negates cos -- sign flips are XORs of the
+  // sign bit; outside the documented domain the result is NaN (loud), never silently wrong
+  const bool ok = (fm_hi(x) & 0x7fffffff) < 0x41d00000;  // |x| < 2^30, false for NaN/inf
   const double ss = (q & 1) ? c0 : s0;
   const double cc = (q & 1) ? s0 : c0;
-  // outside the documented domain the result is NaN (loud), never a silently wrong number
-  const bool ok = fabs(x) < 1073741824.0;
-  *sn = ok ? ((q & 2) ? -ss : ss) : NAN;
-  *cs = ok ? (((q + 1) & 2) ? -cc : cc) : NAN;
+  const int bad = ok ? 0 : 0x7ff80000;
+  *sn = fm_make((fm_hi(ss) ^ ((q & 2) << 30)) | bad, fm_lo(ss));
+  *cs = fm_make((fm_hi(cc) ^ (((q + 1) & 2) << 30)) | bad, fm_lo(cc));
 }
 
 // log(x), x > 0 and normal (callers scale; no special cases)
@@ -199,7 +201,9 @@ FM_HD double fm_atan2(double y, double x) {
   // bring tiny (incl. subnormal: rcp.approx flushes them) or huge pairs into the safe range;
   // powers of two, so the ratio is unchanged
   const double top = ax > ay ? ax : ay;
-  const double sc = top < 1e-150 ? 0x1p600 : (top > 1e150 ? 0x1p-600 : 1.0);
+  int e = ((fm_hi(top) >> 20) & 0x7ff) - 1023;
+  e = e < -1020 ? -1020 : (e > 1020 ? 1020 : e);
+  const double sc = fm_make((1023 - e) << 20, 0);  // 2^-e: the larger operand lands in [1, 2)
   ax *= sc;
   ay *= sc;
   const double mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
@@ -218,7 +222,7 @@ FM_HD double fm_atan2(double y, double x) {
   a = big ? (K[10] + (a + K[11])) : a;
   a = ay > ax ? (K[12] - (a - K[13])) : a;
   a = fm_hi(x) < 0 ? (K[14] - (a - K[15])) : a;
-  return fm_hi(y) < 0 ? -a : a;
+  return fm_make(fm_hi(a) ^ (fm_hi(y) & 0x80000000), fm_lo(a));
 }
 
 }  // namespace fop

@@ -81,5 +81,5 @@ if "c5" in which:
     res["c5"] = {"what": f"Heston COS sweep shard P={P} x 8 x 66", "kernels_ms": k, "ms": ms,
                  "prices_per_s": P * 8 * 64 / (ms * 1e-3)}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", os.environ.get("FOP_CONFIGS_OUT", "configs.json")), "w"), indent=1)
 print(json.dumps(res, indent=1))
