@@ -2,11 +2,18 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
-#include "cos_split_kernels.cuh"
+#include "cos_fused_ws.cuh"
 #include "handle.cuh"
+
+namespace fop {  // capi_cos_fused.cu
+int cos_fused_pick_nb(int J);
+int cos_fused_consts(fop_handle_t h, int base, int tc, const double* params, int np, int P, ModelConsts* out);
+int cos_fused_launch(fop_handle_t h, CosFusedArgs& a, int NB);
+}  // namespace fop
 
 namespace {
 using namespace fop;
@@ -48,6 +55,27 @@ double vk_put(double xMin, double u, int k) {
   return phi - chi;
 }
 
+// Common grid of the maturities: T_m = n_m dt with integers 1 <= n_m < 4096, dt = min(T) / q, to
+// within a few ulps (anything looser would change the prices).  Market maturities (weeks, months)
+// are of this form; when they are not, n stays empty and every maturity gets its own exp.
+bool maturity_grid(const std::vector<double>& T, double* dt_out, std::vector<int>* n) {
+  const double tmin = *std::min_element(T.begin(), T.end());
+  if (!(tmin > 0.0) || T.size() < 2) return false;
+  for (int q = 1; q <= 64; ++q) {
+    const double dt = tmin / q;
+    bool ok = true;
+    n->clear();
+    for (double t : T) {
+      const double ratio = t / dt, k = std::nearbyint(ratio);
+      if (k < 1.0 || k >= 4096.0 || std::fabs(ratio - k) > 2e-15 * k) { ok = false; break; }
+      n->push_back((int)k);
+    }
+    if (ok) { *dt_out = dt; return true; }
+  }
+  n->clear();
+  return false;
+}
+
 // kinds[nk]: output kinds (fop_cos_kind); out = [nk][P][M][J] (or nullptr in loss-only mode)
 int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, const double* K_desc,
             int J, double S0, double r, const double* T, int M, int numU, const int* kinds, int nk,
@@ -72,7 +100,20 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
 
   int nblk = 0;
   const GemmVariant* gv = pick_gemm(J, &nblk);
-  const int JB = 8 * gv->NB, Jp = nblk * JB;
+  // Path.  Default: the split path (coefficient kernel, then a GEMM over strike blocks that
+  // re-uses each coefficient nblk times).  FOP_COS_PATH=fused selects, for few strikes and one
+  // output kind, the warp-specialised single kernel of cos_fused_ws.cuh (CF producers + tensor-core
+  // consumers in one CTA, no coefficient matrix in HBM).  It is kept selectable and tested, not
+  // the default: on config 5 it measures 6.4 ms against 3.8 + 2.5 ms for the split path (both
+  // halves want the same fp64 pipe; profiles/README.md).
+  const int fnb = cos_fused_pick_nb(J);
+  const int spt = M <= FW_MAX_M ? FW_ROWS / M : 0;
+  bool fused = false;
+  if (const char* force = std::getenv("FOP_COS_PATH"))
+    fused = !std::strcmp(force, "fused") && nk == 1 && fnb > 0 && spt > 0;
+  if (fused) nblk = 1;
+  const int JB = fused ? 8 * fnb : 8 * gv->NB;
+  const int Jp = fused ? dm_bs(fnb) : nblk * JB;  // row stride of the basis table
   // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
   const int KK = ((2 * numU + DM_KC - 1) / DM_KC) * DM_KC;
 
@@ -82,7 +123,8 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   FOP_CUDA(h, cudaMemcpy(Kh.data(), K_desc, sizeof(double) * J, cudaMemcpyDefault));
   FOP_CUDA(h, cudaMemcpy(Th.data(), T, sizeof(double) * M, cudaMemcpyDefault));
   auto& cc = h->cos_cache;
-  const size_t tab_doubles = 2 * (size_t)numU + 2 * (size_t)J + M;
+  const size_t npow_off = 2 * (size_t)numU + 2 * (size_t)J + M;   // [M] int32 n_m, in M doubles of space
+  const size_t tab_doubles = npow_off + M;
   const bool hit = cc.dev && cc.S0 == S0 && cc.numU == numU && cc.JB == JB && cc.Jp == Jp &&
                    cc.KK == KK && cc.K == Kh && cc.T == Th;
   if (!hit) {
@@ -93,6 +135,12 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     for (int j = 0; j < J; ++j) x[j] = std::log(S0 / Kh[j]);  // getXFromK, OptionPricing.h:110-117
     std::copy(Kh.begin(), Kh.end(), x + J);
     std::copy(Th.begin(), Th.end(), x + 2 * J);
+    cc.dt = 0.0;
+    std::vector<int> npow;
+    if (maturity_grid(Th, &cc.dt, &npow) && !std::getenv("FOP_COS_NO_TGRID"))
+      std::memcpy(tab.data() + npow_off, npow.data(), sizeof(int) * M);
+    else
+      cc.dt = 0.0;
     const double xMin = x[0], xMax = x[J - 1];
     const double du = M_PI / (xMax - xMin), cp = 2.0 / (xMax - xMin);
     for (int k = 0; k < numU; ++k) {
@@ -123,6 +171,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const double* d_tab = cc.dev;
   const double* d_K = cc.dev + 2 * numU + J;
   const double* d_T = cc.dev + 2 * numU + 2 * J;
+  const int* d_npow = cc.dt > 0.0 ? reinterpret_cast<const int*>(cc.dev + npow_off) : nullptr;
   const double* d_basis = cc.dev + ((tab_doubles + 1) & ~(size_t)1);
 
   const bool out_host = out && !is_device_ptr(out);
@@ -130,7 +179,8 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   // Parameter sets are processed in chunks: bounds the coefficient matrix C (4 KiB per row at
   // numU = 256) and the staging of a host-bound price matrix to ~1 GiB each.
   long long chunkP = P;
-  chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * KK * 8 * ngreeks)));
+  if (!fused)
+    chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * KK * 8 * ngreeks)));
   if (out_host) chunkP = std::min<long long>(chunkP, std::max<long long>(1, (1ll << 30) / ((long long)M * J * 8)));
   const long long chunk_rows = chunkP * M;
   const int lossblk = nblk;
@@ -139,7 +189,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   size_t need = stage_bytes(params, (size_t)P * np * 8);
   if (mkt) need += stage_bytes(mkt, (size_t)M * J * 8);
   if (w) need += stage_bytes(w, (size_t)M * J * 8);
-  need += Arena::pad((size_t)chunk_rows * KK * 8 * ngreeks);
+  need += fused ? Arena::pad((size_t)P * sizeof(ModelConsts)) : Arena::pad((size_t)chunk_rows * KK * 8 * ngreeks);
   if (out_host) need += Arena::pad((size_t)chunk_rows * J * 8);
   if (loss) need += Arena::pad((size_t)P * M * lossblk * 8) + (loss_host ? Arena::pad((size_t)P * 8) : 0);
   FOP_TRY(ar.reserve(need));
@@ -148,7 +198,9 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
   if (mkt) FOP_TRY(stage_in(h, ar, mkt, (size_t)M * J, &d_mkt));
   if (w) FOP_TRY(stage_in(h, ar, w, (size_t)M * J, &d_w));
-  double* d_C = ar.alloc<double>((size_t)chunk_rows * KK * ngreeks);
+  double* d_C = fused ? nullptr : ar.alloc<double>((size_t)chunk_rows * KK * ngreeks);
+  ModelConsts* d_consts = fused ? ar.alloc<ModelConsts>(P) : nullptr;
+  if (fused) FOP_TRY(cos_fused_consts(h, model.base, model.time_change, d_params, np, P, d_consts));
   double* d_out_tmp = out_host ? ar.alloc<double>((size_t)chunk_rows * J) : nullptr;
   double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M * lossblk) : nullptr;
   double* d_loss = loss ? (loss_host ? ar.alloc<double>(P) : loss) : nullptr;
@@ -163,6 +215,31 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
     const int pc = (int)std::min<long long>(chunkP, P - p0);
     const long long rows = (long long)pc * M;
+    if (fused) {
+      const int kind = kinds[0];
+      double* out_k = out ? out + (size_t)p0 * M * J : nullptr;
+      CosFusedArgs fa;
+      CosCoeffArgs& ca = fa.ca;
+      ca.base = model.base;  ca.tc = model.time_change;
+      ca.greek_mask = greek_mask;  ca.plane = 0;
+      ca.P = pc;  ca.M = M;  ca.K = numU;  ca.Kp = KK / 2;  ca.np = np;  ca.spb = 0;
+      ca.r = r;
+      ca.params = d_params + (size_t)p0 * np;
+      ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = nullptr;
+      fa.kind = kind;  fa.J = J;  fa.nchunks = KK / FW_KC;  fa.SPT = spt;  fa.depth = 0;
+      fa.S0 = S0;
+      fa.consts = d_consts + p0;
+      fa.basis = d_basis;  fa.strikes = d_K;
+      fa.out = out ? (out_host ? d_out_tmp : out_k) : nullptr;
+      fa.vec2 = (J % 2 == 0) && (reinterpret_cast<uintptr_t>(fa.out) % 16 == 0);
+      fa.mkt = d_mkt;  fa.w = d_w;
+      fa.rowloss = loss ? d_rowloss + (size_t)p0 * M : nullptr;
+      FOP_TRY(cos_fused_launch(h, fa, fnb));
+      if (out_host)
+        FOP_CUDA(h, cudaMemcpyAsync(out_k, d_out_tmp, (size_t)rows * J * 8, cudaMemcpyDeviceToHost,
+                                    h->stream));
+      continue;
+    }
     {
       CosCoeffArgs ca;
       ca.base = model.base;  ca.tc = model.time_change;
@@ -171,13 +248,15 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ca.spb = std::max(1, std::min(COEFF_MAX_SPB, 1024 / ca.Kp));
       ca.r = r;
       ca.params = d_params + (size_t)p0 * np;
-      ca.T = d_T;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = d_C;
+      ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = d_C;
       const int ngroups = (pc + ca.spb - 1) / ca.spb;
       const int cgrid = std::min(ngroups, h->sm_count * 32);
       {
         ProfScope ps(h, "cos_coeff_kernel");
-        if (M >= 4) cos_coeff_kernel<4><<<cgrid, 256, 0, h->stream>>>(ca);
-        else if (M >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
+        int ilp = M >= 2 ? 2 : 1;  // measured: 2 maturities interleaved beat 1 and 4 (register cap 128)
+        if (const char* e = std::getenv("FOP_COEFF_ILP")) ilp = std::max(1, std::min(atoi(e), M >= 4 ? 4 : M >= 2 ? 2 : 1));
+        if (ilp >= 4) cos_coeff_kernel<4><<<cgrid, 256, 0, h->stream>>>(ca);
+        else if (ilp >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
         else cos_coeff_kernel<1><<<cgrid, 256, 0, h->stream>>>(ca);
       }
       FOP_LAUNCH_CHECK(h);

@@ -150,25 +150,33 @@ enum { CF_MODE_LEVY = 0, CF_MODE_CIR = 1, CF_MODE_DET = 2 };
 __device__ __forceinline__ int cf_mode(int tc, const ModelConsts& c) {
   return tc == TC_NONE ? CF_MODE_LEVY : (c.adaV == 0.0 ? CF_MODE_DET : CF_MODE_CIR);
 }
-template <int MODE>
-__device__ __forceinline__ cd cf_log_at_mode(const ModelConsts& c, const CfPre& pre, double T) {
-  const cd l = mk(pre.lin.x * T, pre.lin.y * T);
+// CIR clock, given e = exp(-delta T) (computed directly, or as a power of exp(-delta dt) when the
+// maturities sit on a common grid, see coeff_maturities) and l = lin * T
+template <class T>
+__device__ __forceinline__ cx<T> cf_log_cir_given_e(const ModelConsts& c, const CfPre& pre, T Tm,
+                                                    cx<T> l, cx<T> e) {
+  const cx<T> ome = 1.0 - e;
+  const cx<T> w = 1.0 - pre.g * ome;
+  const cx<T> b = pre.pod * cdiv(ome, w);
+  const cx<T> lw = clog(w);
+  const cx<T> cc = mk(c.aos2 * (2.0 * lw.x + pre.dmk.x * Tm), c.aos2 * (2.0 * lw.y + pre.dmk.y * Tm));
+  return l - (c.v0 * b) - cc;
+}
+
+// T = double, or VD<N>: N maturities of the same (set, u) pair advanced operation by operation
+template <int MODE, class T>
+__device__ __forceinline__ cx<T> cf_log_at_mode(const ModelConsts& c, const CfPre& pre, T Tm) {
+  const cx<T> l = mk(pre.lin.x * Tm, pre.lin.y * Tm);
   if (MODE == CF_MODE_LEVY) return l;
   if (MODE == CF_MODE_DET) {
     const cd kp = pre.delta, ps = pre.pod;
-    const cd ek = 1.0 - cexp(mk(-kp.x * T, -kp.y * T));
-    const cd ekk = cdiv(ek, kp);
-    const cd b = ps * ekk;
-    const cd cc = cdiv(mk(c.speed * ps.x, c.speed * ps.y), kp) * (T - ekk);
+    const cx<T> ek = 1.0 - cexp(mk(-kp.x * Tm, -kp.y * Tm));
+    const cx<T> ekk = cdiv(ek, kp);
+    const cx<T> b = ps * ekk;
+    const cx<T> cc = cdiv(mk(c.speed * ps.x, c.speed * ps.y), kp) * (Tm - ekk);
     return l - (c.v0 * b) - cc;
   }
-  const cd e = cexp(mk(-pre.delta.x * T, -pre.delta.y * T));
-  const cd ome = 1.0 - e;
-  const cd w = 1.0 - pre.g * ome;
-  const cd b = pre.pod * cdiv(ome, w);
-  const cd lw = clog(w);
-  const cd cc = mk(c.aos2 * (2.0 * lw.x + pre.dmk.x * T), c.aos2 * (2.0 * lw.y + pre.dmk.y * T));
-  return l - (c.v0 * b) - cc;
+  return cf_log_cir_given_e(c, pre, Tm, l, cexp(mk(-pre.delta.x * Tm, -pre.delta.y * Tm)));
 }
 __device__ __forceinline__ cd cf_log_at(int tc, const ModelConsts& c, const CfPre& pre, double T) {
   const int mode = cf_mode(tc, c);
@@ -178,15 +186,16 @@ __device__ __forceinline__ cd cf_log_at(int tc, const ModelConsts& c, const CfPr
 }
 
 // Option transforms applied to phi(u) (OptionPricing.h:44-73): 0 price, 1 delta, 2 gamma, 3 theta
-__device__ __forceinline__ cd option_transform(int greek, cd phi, cd u, double r) {
+template <class T>
+__device__ __forceinline__ cx<T> option_transform(int greek, cx<T> phi, cd u, double r) {
   if (greek == 0) return phi;
   if (greek == 1) return phi * u;
   if (greek == 2) return -(phi * (u * (1.0 - u)));
   // theta; log of the CF VALUE (principal branch), as the reference does; select, not branch
-  const cd l = clog(phi);
-  const cd t = -(mk(l.x - r, l.y) * phi);
-  const bool pos = phi.x > 0.0;
-  return mk(pos ? t.x : 0.0, pos ? t.y : 0.0);
+  const cx<T> l = clog(phi);
+  const cx<T> t = -(mk(l.x - r, l.y) * phi);
+  const auto pos = phi.x > 0.0;
+  return mk(fm_sel(pos, t.x, 0.0), fm_sel(pos, t.y, 0.0));
 }
 
 }  // namespace fop

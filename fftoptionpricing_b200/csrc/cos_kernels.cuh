@@ -29,7 +29,7 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // basis[2k][j] = cos(u_k (x_j - xMin)), basis[2k+1][j] = -sin(u_k (x_j - xMin)); 0 for j >= J
-__global__ void cos_basis_kernel(const double* __restrict__ uk, const double* __restrict__ x,
+static __global__ void cos_basis_kernel(const double* __restrict__ uk, const double* __restrict__ x,
                                  int K, int J, int Jp, double* __restrict__ basis) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= K * Jp) return;

@@ -8,42 +8,47 @@
 
 namespace fop {
 
-struct cd {
-  double x, y;
-};
+// cx<T>: complex number over T = double or T = VD<N> (N independent values, see fmath.cuh).
+// Mixed operations broadcast the scalar operand.
+template <class T> struct cx { T x, y; };
+using cd = cx<double>;
+#define CX_HD __host__ __device__ __forceinline__
 
-__host__ __device__ __forceinline__ cd mk(double x, double y) { cd r; r.x = x; r.y = y; return r; }
-__host__ __device__ __forceinline__ cd operator+(cd a, cd b) { return mk(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ cd operator-(cd a, cd b) { return mk(a.x - b.x, a.y - b.y); }
-__host__ __device__ __forceinline__ cd operator-(cd a) { return mk(-a.x, -a.y); }
-__host__ __device__ __forceinline__ cd operator*(cd a, cd b) {
+template <class T> CX_HD cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
+template <class A, class B> CX_HD auto operator+(cx<A> a, cx<B> b) -> cx<decltype(a.x + b.x)> { return mk(a.x + b.x, a.y + b.y); }
+template <class A, class B> CX_HD auto operator-(cx<A> a, cx<B> b) -> cx<decltype(a.x - b.x)> { return mk(a.x - b.x, a.y - b.y); }
+template <class A> CX_HD cx<A> operator-(cx<A> a) { return mk(-a.x, -a.y); }
+template <class A, class B> CX_HD auto operator*(cx<A> a, cx<B> b) -> cx<decltype(a.x * b.x)> {
   return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__host__ __device__ __forceinline__ cd operator*(double s, cd a) { return mk(s * a.x, s * a.y); }
-__host__ __device__ __forceinline__ cd operator*(cd a, double s) { return mk(s * a.x, s * a.y); }
-__host__ __device__ __forceinline__ cd operator+(cd a, double s) { return mk(a.x + s, a.y); }
-__host__ __device__ __forceinline__ cd operator+(double s, cd a) { return mk(a.x + s, a.y); }
-__host__ __device__ __forceinline__ cd operator-(cd a, double s) { return mk(a.x - s, a.y); }
-__host__ __device__ __forceinline__ cd operator-(double s, cd a) { return mk(s - a.x, -a.y); }
-__host__ __device__ __forceinline__ cd conj(cd a) { return mk(a.x, -a.y); }
-__host__ __device__ __forceinline__ double norm(cd a) { return a.x * a.x + a.y * a.y; }
+template <class A> CX_HD cx<A> operator*(double s, cx<A> a) { return mk(s * a.x, s * a.y); }
+template <class A> CX_HD cx<A> operator*(cx<A> a, double s) { return mk(s * a.x, s * a.y); }
+template <int N, class A> CX_HD cx<VD<N>> operator*(VD<N> s, cx<A> a) { return mk(s * a.x, s * a.y); }
+template <int N, class A> CX_HD cx<VD<N>> operator*(cx<A> a, VD<N> s) { return mk(s * a.x, s * a.y); }
+template <class A> CX_HD cx<A> operator+(cx<A> a, double s) { return mk(a.x + s, a.y); }
+template <class A> CX_HD cx<A> operator+(double s, cx<A> a) { return mk(a.x + s, a.y); }
+template <class A> CX_HD cx<A> operator-(cx<A> a, double s) { return mk(a.x - s, a.y); }
+template <class A> CX_HD cx<A> operator-(double s, cx<A> a) { return mk(s - a.x, -a.y); }
+template <int N> CX_HD cx<VD<N>> operator-(VD<N> s, cx<VD<N>> a) { return mk(s - a.x, -a.y); }
+template <class A> CX_HD cx<A> conj(cx<A> a) { return mk(a.x, -a.y); }
+template <class A> CX_HD A norm(cx<A> a) { return a.x * a.x + a.y * a.y; }
 
-__host__ __device__ __forceinline__ cd cdiv(cd a, cd b) {
-  const double inv = fm_rcp(b.x * b.x + b.y * b.y);
+template <class A, class B> CX_HD auto cdiv(cx<A> a, cx<B> b) -> cx<decltype(a.x * b.x)> {
+  const B inv = fm_rcp(b.x * b.x + b.y * b.y);
   return mk((a.x * b.x + a.y * b.y) * inv, (a.y * b.x - a.x * b.y) * inv);
 }
-__host__ __device__ __forceinline__ cd cdiv(cd a, double s) { return mk(a.x / s, a.y / s); }
+CX_HD cd cdiv(cd a, double s) { return mk(a.x / s, a.y / s); }
 
 // The complex elementary functions below are straight-line code over fmath.cuh (no branches, no
-// libdevice calls), so several independent evaluations interleave in one basic block.
-__host__ __device__ __forceinline__ cd cexp(cd z) {
-  const double e = fm_exp(z.x);
-  double s, c;
+// libdevice calls); with T = VD<N> the N evaluations advance operation by operation.
+template <class T> CX_HD cx<T> cexp(cx<T> z) {
+  const T e = fm_exp(z.x);
+  T s, c;
   fm_sincos(z.y, &s, &c);
   return mk(e * c, e * s);
 }
 // e^{i t}
-__host__ __device__ __forceinline__ cd cis(double t) {
+CX_HD cd cis(double t) {
   double s, c;
   fm_sincos(t, &s, &c);
   return mk(c, s);
@@ -51,16 +56,16 @@ __host__ __device__ __forceinline__ cd cis(double t) {
 // principal log: Im in (-pi, pi].  |z| is formed after scaling by a power of two so that tiny or
 // huge CF values (FSTS theta takes log of phi ~ 1e-200) neither underflow nor overflow, matching
 // libstdc++'s log(hypot(x, y)).  z = 0 gives -inf.
-__host__ __device__ __forceinline__ cd clog(cd z) {
-  const double ax = fabs(z.x), ay = fabs(z.y);
-  const double big = ax > ay ? ax : ay;
-  int e = ((fm_hi(big) >> 20) & 0x7ff) - 1023;
-  e = e < -1020 ? -1020 : (e > 1020 ? 1020 : e);
-  const double sc = fm_make((1023 - e) << 20, 0);  // 2^-e, exact
-  const double xs = z.x * sc, ys = z.y * sc;
-  const double n = fm_fma(xs, xs, ys * ys);
-  const double lr = fm_fma((double)e, FM_TAB(fm_k)[16], 0.5 * fm_log_pos(n));
-  return mk(big == 0.0 ? -INFINITY : lr, fm_atan2(z.y, z.x));
+template <class T> CX_HD cx<T> clog(cx<T> z) {
+  const T ax = fm_abs(z.x), ay = fm_abs(z.y);
+  const T big = fm_sel(ax > ay, ax, ay);
+  auto e = ((fm_hi(big) >> 20) & 0x7ff) - 1023;
+  e = fm_sel(e < -1020, -1020, fm_sel(e > 1020, 1020, e));
+  const T sc = fm_make((1023 - e) << 20, 0);  // 2^-e, exact
+  const T xs = z.x * sc, ys = z.y * sc;
+  const T n = fm_fma(xs, xs, ys * ys);
+  const T lr = fm_fma(fm_i2d(e), FM_TAB(fm_k)[16], 0.5 * fm_log_pos(n));
+  return mk(fm_sel(big == 0.0, -(double)INFINITY, lr), fm_atan2(z.y, z.x));
 }
 // principal square root (Re >= 0; on the negative real axis the sign of Im follows the sign of z.y)
 __device__ __forceinline__ cd csqrt(cd z) {

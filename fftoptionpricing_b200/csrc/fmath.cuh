@@ -6,8 +6,13 @@
 // of the library routines stop the scheduler from interleaving independent evaluations.  Here
 //   * coefficients live in __constant__ memory (one LDCU.128 fetches two of them into uniform
 //     registers that DFMA reads directly),
-//   * every routine is straight-line code (selects instead of branches), so ILP copies of a
-//     characteristic-function evaluation interleave in one basic block,
+//   * every routine is straight-line code (selects instead of branches) and is a template over the
+//     value type: double, or VD<N> = N independent values processed operation by operation.  The
+//     warp scheduler issues in program order and a dependent DFMA can issue only every 8.4 cycles
+//     (scripts/ub/ub_latency.cu: 1 chain x 4 warps/SMSP reaches 63 % of the fp64 pipe, 4 chains
+//     90 %), and ptxas does not interleave independent call chains on its own
+//     (profiles/r1_cos_fused_v1_sass_stalls.txt: Horner chains issued back to back) -- so the
+//     interleaving of N evaluations is written into the source,
 //   * accuracy is <= ~1.5 ulp on the domains the pricers use (tests/test_fmath_host.py measures
 //     it against long double), far inside the 1e-10 parity budget.
 // Polynomials: exp -- Chebyshev-economised fit of (e^r - 1 - r)/r^2 on |r| <= ln2/2 (error 1.4e-18,
@@ -23,11 +28,13 @@ namespace fop {
 
 #ifdef __CUDA_ARCH__
 #define FM_TAB(name) name##_d
-#define FM_DECL(name, ...) static __constant__ double name##_d[] = {__VA_ARGS__};
 #else
 #define FM_TAB(name) name##_h
-#define FM_DECL(name, ...) static const double name##_h[] = {__VA_ARGS__};
 #endif
+// (Tried and dropped: a shared-memory copy of the tables read by volatile LDS at each use removes
+// the MOV.SPILL / R2UR.FILL traffic ptxas generates around its uniform-register copies of the
+// coefficients -- 17 % of the issued instructions -- but the kernels time the same within 1 %.)
+#define FM_TABPTR const double*
 // both copies are needed in a translation unit that compiles host and device passes
 #define FM_TABLE(name, ...)                                   \
   static __constant__ double name##_d[] = {__VA_ARGS__};      \
@@ -76,6 +83,49 @@ FM_TABLE(fm_k, 1.4426950408889634,        // 0  log2(e)
 
 #define FM_HD __host__ __device__ __forceinline__
 
+
+// ---- N-wide value types: every operation is a loop over N independent lanes --------------------
+template <int N> struct VD { double v[N]; };
+template <int N> struct VI { int v[N]; };
+template <int N> struct VB { bool v[N]; };
+
+#define FM_LANES _Pragma("unroll") for (int i_ = 0; i_ < N; ++i_)
+#define FM_VD_BINOP(op)                                                                             \
+  template <int N> FM_HD VD<N> operator op(VD<N> a, VD<N> b) { VD<N> r; FM_LANES r.v[i_] = a.v[i_] op b.v[i_]; return r; } \
+  template <int N> FM_HD VD<N> operator op(VD<N> a, double b) { VD<N> r; FM_LANES r.v[i_] = a.v[i_] op b; return r; }      \
+  template <int N> FM_HD VD<N> operator op(double a, VD<N> b) { VD<N> r; FM_LANES r.v[i_] = a op b.v[i_]; return r; }
+FM_VD_BINOP(+) FM_VD_BINOP(-) FM_VD_BINOP(*)
+#undef FM_VD_BINOP
+template <int N> FM_HD VD<N> operator-(VD<N> a) { VD<N> r; FM_LANES r.v[i_] = -a.v[i_]; return r; }
+#define FM_VD_CMP(op)                                                                               \
+  template <int N> FM_HD VB<N> operator op(VD<N> a, VD<N> b) { VB<N> r; FM_LANES r.v[i_] = a.v[i_] op b.v[i_]; return r; } \
+  template <int N> FM_HD VB<N> operator op(VD<N> a, double b) { VB<N> r; FM_LANES r.v[i_] = a.v[i_] op b; return r; }
+FM_VD_CMP(>) FM_VD_CMP(<) FM_VD_CMP(==) FM_VD_CMP(>=)
+#undef FM_VD_CMP
+#define FM_VI_BINOP(op)                                                                             \
+  template <int N> FM_HD VI<N> operator op(VI<N> a, VI<N> b) { VI<N> r; FM_LANES r.v[i_] = a.v[i_] op b.v[i_]; return r; } \
+  template <int N> FM_HD VI<N> operator op(VI<N> a, int b) { VI<N> r; FM_LANES r.v[i_] = a.v[i_] op b; return r; }         \
+  template <int N> FM_HD VI<N> operator op(int a, VI<N> b) { VI<N> r; FM_LANES r.v[i_] = a op b.v[i_]; return r; }
+FM_VI_BINOP(+) FM_VI_BINOP(-) FM_VI_BINOP(&) FM_VI_BINOP(|) FM_VI_BINOP(^) FM_VI_BINOP(>>) FM_VI_BINOP(<<)
+#undef FM_VI_BINOP
+#define FM_VI_CMP(op)                                                                               \
+  template <int N> FM_HD VB<N> operator op(VI<N> a, int b) { VB<N> r; FM_LANES r.v[i_] = a.v[i_] op b; return r; }
+FM_VI_CMP(>) FM_VI_CMP(<) FM_VI_CMP(!=)
+#undef FM_VI_CMP
+template <int N> FM_HD VB<N> operator&&(VB<N> a, VB<N> b) { VB<N> r; FM_LANES r.v[i_] = a.v[i_] && b.v[i_]; return r; }
+
+// select (the scalar forms compile to the same FSEL / SEL as a ternary)
+FM_HD double fm_sel(bool c, double a, double b) { return c ? a : b; }
+FM_HD int fm_sel(bool c, int a, int b) { return c ? a : b; }
+template <int N> FM_HD VD<N> fm_sel(VB<N> c, VD<N> a, VD<N> b) { VD<N> r; FM_LANES r.v[i_] = c.v[i_] ? a.v[i_] : b.v[i_]; return r; }
+template <int N> FM_HD VD<N> fm_sel(VB<N> c, VD<N> a, double b) { VD<N> r; FM_LANES r.v[i_] = c.v[i_] ? a.v[i_] : b; return r; }
+template <int N> FM_HD VD<N> fm_sel(VB<N> c, double a, VD<N> b) { VD<N> r; FM_LANES r.v[i_] = c.v[i_] ? a : b.v[i_]; return r; }
+template <int N> FM_HD VD<N> fm_sel(VB<N> c, double a, double b) { VD<N> r; FM_LANES r.v[i_] = c.v[i_] ? a : b; return r; }
+template <int N> FM_HD VI<N> fm_sel(VB<N> c, VI<N> a, VI<N> b) { VI<N> r; FM_LANES r.v[i_] = c.v[i_] ? a.v[i_] : b.v[i_]; return r; }
+template <int N> FM_HD VI<N> fm_sel(VB<N> c, VI<N> a, int b) { VI<N> r; FM_LANES r.v[i_] = c.v[i_] ? a.v[i_] : b; return r; }
+template <int N> FM_HD VI<N> fm_sel(VB<N> c, int a, VI<N> b) { VI<N> r; FM_LANES r.v[i_] = c.v[i_] ? a : b.v[i_]; return r; }
+template <int N> FM_HD VI<N> fm_sel(VB<N> c, int a, int b) { VI<N> r; FM_LANES r.v[i_] = c.v[i_] ? a : b; return r; }
+
 FM_HD int fm_hi(double x) {
 #ifdef __CUDA_ARCH__
   return __double2hiint(x);
@@ -98,131 +148,162 @@ FM_HD double fm_make(int hi, int lo) {
 #endif
 }
 FM_HD double fm_fma(double a, double b, double c) { return fma(a, b, c); }
-
-// approximate reciprocal (>= 20 bits) refined to full precision; b normal, nonzero
-FM_HD double fm_rcp(double b) {
+FM_HD double fm_abs(double x) { return fabs(x); }
+FM_HD double fm_i2d(int k) { return (double)k; }
+FM_HD double fm_rcp_seed(double b) {  // >= 20 correct bits; b normal, nonzero
 #ifdef __CUDA_ARCH__
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  return r;
 #else
-  double r = 1.0 / b;  // host build is a test harness only
+  return 1.0 / b;  // host build is a test harness only
 #endif
-  double e = fm_fma(-b, r, 1.0);
+}
+FM_HD double fm_sqrt(double x) { return sqrt(x); }
+
+template <int N> FM_HD VI<N> fm_hi(VD<N> x) { VI<N> r; FM_LANES r.v[i_] = fm_hi(x.v[i_]); return r; }
+template <int N> FM_HD VI<N> fm_lo(VD<N> x) { VI<N> r; FM_LANES r.v[i_] = fm_lo(x.v[i_]); return r; }
+template <int N> FM_HD VD<N> fm_make(VI<N> hi, VI<N> lo) { VD<N> r; FM_LANES r.v[i_] = fm_make(hi.v[i_], lo.v[i_]); return r; }
+template <int N> FM_HD VD<N> fm_make(VI<N> hi, int lo) { VD<N> r; FM_LANES r.v[i_] = fm_make(hi.v[i_], lo); return r; }
+template <int N> FM_HD VD<N> fm_abs(VD<N> x) { VD<N> r; FM_LANES r.v[i_] = fabs(x.v[i_]); return r; }
+template <int N> FM_HD VD<N> fm_i2d(VI<N> k) { VD<N> r; FM_LANES r.v[i_] = (double)k.v[i_]; return r; }
+template <int N> FM_HD VD<N> fm_rcp_seed(VD<N> b) { VD<N> r; FM_LANES r.v[i_] = fm_rcp_seed(b.v[i_]); return r; }
+template <int N> FM_HD VD<N> fm_sqrt(VD<N> x) { VD<N> r; FM_LANES r.v[i_] = sqrt(x.v[i_]); return r; }
+#define FM_VD_FMA(TA, TB, TC, ea, eb, ec)                                                           \
+  template <int N> FM_HD VD<N> fm_fma(TA a, TB b, TC c) { VD<N> r; FM_LANES r.v[i_] = fma(ea, eb, ec); return r; }
+FM_VD_FMA(VD<N>, VD<N>, VD<N>, a.v[i_], b.v[i_], c.v[i_])
+FM_VD_FMA(VD<N>, VD<N>, double, a.v[i_], b.v[i_], c)
+FM_VD_FMA(VD<N>, double, VD<N>, a.v[i_], b, c.v[i_])
+FM_VD_FMA(double, VD<N>, VD<N>, a, b.v[i_], c.v[i_])
+FM_VD_FMA(VD<N>, double, double, a.v[i_], b, c)
+FM_VD_FMA(double, VD<N>, double, a, b.v[i_], c)
+#undef FM_VD_FMA
+template <int N> FM_HD VD<N> fm_bcast(double x, VD<N>) { VD<N> r; FM_LANES r.v[i_] = x; return r; }
+FM_HD double fm_bcast(double x, double) { return x; }
+
+// reciprocal to full precision from the hardware seed (two Newton steps); b normal, nonzero
+template <class T> FM_HD T fm_rcp(T b) {
+  T r = fm_rcp_seed(b);
+  T e = fm_fma(-b, r, 1.0);
   r = fm_fma(r, e, r);
   e = fm_fma(-b, r, 1.0);
   r = fm_fma(r, e, r);
   return r;
 }
 // a / b to <= 1 ulp for normal-range operands
-FM_HD double fm_div(double a, double b) {
-  const double r = fm_rcp(b);
-  const double q = a * r;
+template <class T> FM_HD T fm_div(T a, T b) {
+  const T r = fm_rcp(b);
+  const T q = a * r;
   return fm_fma(fm_fma(-b, q, a), r, q);
 }
 
-FM_HD double fm_exp(double x) {
-  const double* K = FM_TAB(fm_k);
+template <class T> FM_HD T fm_exp(T x) {
+  FM_TABPTR K = FM_TAB(fm_k);
   // one magnitude clamp (keeps NaN: the comparison is false) so that k below fits an int
-  x = fabs(x) > 1.0e6 ? copysign(1.0e6, x) : x;
+  x = fm_sel(fm_abs(x) > 1.0e6, fm_make((fm_hi(x) & 0x80000000) | 0x412e8480, 0), x);  // +-1e6
   const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-  const double t = fm_fma(x, K[0], MAGIC);
-  int k = fm_lo(t);
-  const double kd = t - MAGIC;
-  double r = fm_fma(kd, K[1], x);   // ln2 hi
+  const T t = fm_fma(x, K[0], MAGIC);
+  auto k = fm_lo(t);
+  const T kd = t - MAGIC;
+  T r = fm_fma(kd, K[1], x);   // ln2 hi
   r = fm_fma(kd, K[2], r);   // ln2 lo
-  const double* c = FM_TAB(fm_exp_q);
-  double q = c[0];
+  FM_TABPTR c = FM_TAB(fm_exp_q);
+  T q = fm_fma(r, c[0], c[1]);
 #pragma unroll
-  for (int i = 1; i <= 10; ++i) q = fm_fma(q, r, c[i]);
-  const double p = fm_fma(r * r, q, r) + 1.0;
+  for (int i = 2; i <= 10; ++i) q = fm_fma(q, r, c[i]);
+  const T p = fm_fma(r * r, q, r) + 1.0;
   // scale by 2^k in two normal steps; |k| clamped to 1100 -> exact 0 / inf outside the range
-  k = k < -1100 ? -1100 : (k > 1100 ? 1100 : k);
-  const int k1 = k >> 1, k2 = k - k1;
+  k = fm_sel(k < -1100, -1100, fm_sel(k > 1100, 1100, k));
+  const auto k1 = k >> 1, k2 = k - k1;
   return (p * fm_make((1023 + k1) << 20, 0)) * fm_make((1023 + k2) << 20, 0);
 }
 
 // sin and cos of x, |x| < 2^30
-FM_HD void fm_sincos(double x, double* sn, double* cs) {
-  const double* K = FM_TAB(fm_k);
+template <class T> FM_HD void fm_sincos(T x, T* sn, T* cs) {
+  FM_TABPTR K = FM_TAB(fm_k);
   const double MAGIC = 6755399441055744.0;
-  const double t = fm_fma(x, K[3], MAGIC);  // 2/pi
-  const int q = fm_lo(t);
-  const double qd = t - MAGIC;
-  double r = fm_fma(qd, K[4], x);   // pi/2 in three parts
+  const T t = fm_fma(x, K[3], MAGIC);  // 2/pi
+  const auto q = fm_lo(t);
+  const T qd = t - MAGIC;
+  T r = fm_fma(qd, K[4], x);   // pi/2 in three parts
   r = fm_fma(qd, K[5], r);
   r = fm_fma(qd, K[6], r);
-  const double z = r * r;
-  const double* S = FM_TAB(fm_sin_s);
-  const double* C = FM_TAB(fm_cos_c);
-  double ps = S[0], pc = C[0];
+  const T z = r * r;
+  FM_TABPTR S = FM_TAB(fm_sin_s);
+  FM_TABPTR C = FM_TAB(fm_cos_c);
+  T ps = fm_fma(z, S[0], S[1]), pc = fm_fma(z, C[0], C[1]);
 #pragma unroll
-  for (int i = 1; i < 6; ++i) {
+  for (int i = 2; i < 6; ++i) {
     ps = fm_fma(ps, z, S[i]);
     pc = fm_fma(pc, z, C[i]);
   }
-  const double s0 = fm_fma(r * z, ps, r);
-  const double c0 = fm_fma(z * z, pc, fm_fma(-0.5, z, 1.0));
+  const T s0 = fm_fma(r * z, ps, r);
+  const T c0 = fm_fma(z * z, pc, fm_fma(z, -0.5, 1.0));
   // quadrant: q&1 swaps, (q&2) negates sin, ((q+1)&2) negates cos -- sign flips are XORs of the
   // sign bit; outside the documented domain the result is NaN (loud), never silently wrong
-  const bool ok = (fm_hi(x) & 0x7fffffff) < 0x41d00000;  // |x| < 2^30, false for NaN/inf
-  const double ss = (q & 1) ? c0 : s0;
-  const double cc = (q & 1) ? s0 : c0;
-  const int bad = ok ? 0 : 0x7ff80000;
+  const auto ok = (fm_hi(x) & 0x7fffffff) < 0x41d00000;  // |x| < 2^30, false for NaN/inf
+  const auto odd = (q & 1) != 0;
+  const T ss = fm_sel(odd, c0, s0);
+  const T cc = fm_sel(odd, s0, c0);
+  const auto bad = fm_sel(ok, 0, 0x7ff80000);
   *sn = fm_make((fm_hi(ss) ^ ((q & 2) << 30)) | bad, fm_lo(ss));
   *cs = fm_make((fm_hi(cc) ^ (((q + 1) & 2) << 30)) | bad, fm_lo(cc));
 }
 
 // log(x), x > 0 and normal (callers scale; no special cases)
-FM_HD double fm_log_pos(double x) {
-  const double* K = FM_TAB(fm_k);
-  int hx = fm_hi(x);
-  const int lx = fm_lo(x);
-  const int k = (hx - 0x3fe6a09e) >> 20;  // x = 2^k m, m in [sqrt(1/2), sqrt(2))
-  hx -= k << 20;
-  const double m = fm_make(hx, lx);
-  const double f = m - 1.0;
-  const double s = fm_div(f, 2.0 + f);
-  const double z = s * s;
-  const double* L = FM_TAB(fm_log_lg);
-  double R = L[0];
+template <class T> FM_HD T fm_log_pos(T x) {
+  FM_TABPTR K = FM_TAB(fm_k);
+  auto hx = fm_hi(x);
+  const auto lx = fm_lo(x);
+  const auto k = (hx - 0x3fe6a09e) >> 20;  // x = 2^k m, m in [sqrt(1/2), sqrt(2))
+  hx = hx - (k << 20);
+  const T m = fm_make(hx, lx);
+  const T f = m - 1.0;
+  const T s = fm_div(f, 2.0 + f);
+  const T z = s * s;
+  FM_TABPTR L = FM_TAB(fm_log_lg);
+  T R = fm_fma(z, L[0], L[1]);
 #pragma unroll
-  for (int i = 1; i < 7; ++i) R = fm_fma(R, z, L[i]);
-  R *= z;
-  const double hfsq = 0.5 * f * f;
-  const double dk = (double)k;
+  for (int i = 2; i < 7; ++i) R = fm_fma(R, z, L[i]);
+  R = R * z;
+  const T hfsq = 0.5 * f * f;
+  const T dk = fm_i2d(k);
   // k ln2_hi - ((hfsq - (s (hfsq + R) + k ln2_lo)) - f)
   return fm_fma(dk, K[7], -((hfsq - fm_fma(s, hfsq + R, dk * K[8])) - f));
 }
 
 // atan2(y, x), finite arguments; (0, 0) -> 0 or pi like the C library
-FM_HD double fm_atan2(double y, double x) {
-  const double* K = FM_TAB(fm_k);
-  double ax = fabs(x), ay = fabs(y);
+template <class T> FM_HD T fm_atan2(T y, T x) {
+  FM_TABPTR K = FM_TAB(fm_k);
+  T ax = fm_abs(x), ay = fm_abs(y);
   // bring tiny (incl. subnormal: rcp.approx flushes them) or huge pairs into the safe range;
   // powers of two, so the ratio is unchanged
-  const double top = ax > ay ? ax : ay;
-  int e = ((fm_hi(top) >> 20) & 0x7ff) - 1023;
-  e = e < -1020 ? -1020 : (e > 1020 ? 1020 : e);
-  const double sc = fm_make((1023 - e) << 20, 0);  // 2^-e: the larger operand lands in [1, 2)
-  ax *= sc;
-  ay *= sc;
-  const double mx = ax > ay ? ax : ay, mn = ax > ay ? ay : ax;
-  const bool big = mn > K[9] * mx;  // tan(pi/8)
-  const double num = big ? mn - mx : mn;
-  double den = big ? mn + mx : mx;
-  den = den == 0.0 ? 1.0 : den;  // atan2(0, 0): t = 0
-  const double t = fm_div(num, den);
-  const double z = t * t;
-  const double* A = FM_TAB(fm_atan_t);
-  double p = A[0];
+  const T top = fm_sel(ax > ay, ax, ay);
+  auto e = ((fm_hi(top) >> 20) & 0x7ff) - 1023;
+  e = fm_sel(e < -1020, -1020, fm_sel(e > 1020, 1020, e));
+  const T sc = fm_make((1023 - e) << 20, 0);  // 2^-e: the larger operand lands in [1, 2)
+  ax = ax * sc;
+  ay = ay * sc;
+  const auto xbig = ax > ay;
+  const T mx = fm_sel(xbig, ax, ay), mn = fm_sel(xbig, ay, ax);
+  const auto big = mn > K[9] * mx;  // tan(pi/8)
+  const T num = fm_sel(big, mn - mx, mn);
+  T den = fm_sel(big, mn + mx, mx);
+  den = fm_sel(den == 0.0, 1.0, den);  // atan2(0, 0): t = 0
+  const T t = fm_div(num, den);
+  const T z = t * t;
+  FM_TABPTR A = FM_TAB(fm_atan_t);
+  T p = fm_fma(z, A[0], A[1]);
 #pragma unroll
-  for (int i = 1; i < 11; ++i) p = fm_fma(p, z, A[i]);
-  double a = fm_fma(-t, z * p, t);
+  for (int i = 2; i < 11; ++i) p = fm_fma(p, z, A[i]);
+  T a = fm_fma(-t, z * p, t);
   // + pi/4 (hi + lo) when reduced
-  a = big ? (K[10] + (a + K[11])) : a;
-  a = ay > ax ? (K[12] - (a - K[13])) : a;
-  a = fm_hi(x) < 0 ? (K[14] - (a - K[15])) : a;
+  a = fm_sel(big, K[10] + (a + K[11]), a);
+  a = fm_sel(ay > ax, K[12] - (a - K[13]), a);
+  a = fm_sel(fm_hi(x) < 0, K[14] - (a - K[15]), a);
   return fm_make(fm_hi(a) ^ (fm_hi(y) & 0x80000000), fm_lo(a));
 }
+
+#undef FM_LANES
 
 }  // namespace fop

@@ -27,6 +27,7 @@ struct fop_handle_s {
   struct CosCache {
     std::vector<double> K, T;
     double S0 = 0;
+    double dt = 0;          // > 0: maturities on the grid T_m = n_m dt (n_m stored after T)
     int numU = 0, Jp = 0, JB = 0, KK = 0;
     double* dev = nullptr;  // [uk | vk | x | K | T | basis]
     size_t bytes = 0;

@@ -1,0 +1,110 @@
+"""GPU parity tests of the two COS execution paths and of the maturity-grid shortcut.
+
+* split path (default): cos_coeff_kernel + cos_gemm_dmma_kernel;
+* fused path (FOP_COS_PATH=fused): cos_fused_ws_kernel, warp-specialised producers/consumers;
+* maturities on a common grid T_m = n_m dt use exp(-delta T_m) = exp(-delta dt)^{n_m}; off-grid
+  maturities take one exp per maturity.
+All against the oracle (reference FangOostCallPrice etc., OptionPricing.h:358-559) at the
+north-star tolerance 1e-8 + 1e-10 |ref|."""
+import numpy as np
+import pytest
+
+from tests import cases as CASES
+from tests.conftest import assert_parity
+
+pytestmark = pytest.mark.gpu
+
+ON_GRID = list(CASES.C5_T)                      # multiples of 1/12
+OFF_GRID = [0.1, 0.2718281828, 0.7, 1.3]        # no common grid
+WEEKLY = [k / 52.0 for k in (1, 2, 4, 13, 26, 52, 104)]
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import fftoptionpricing_b200 as F
+    eng = F.Engine(0)
+    yield eng
+    eng.close()
+
+
+def _strikes(J, S0=100.0):
+    return np.concatenate([[S0 * 50.0], S0 * np.linspace(1.5, 0.5, J - 2), [S0 * 0.03]])
+
+
+@pytest.mark.parametrize("path", ["split", "fused"])
+@pytest.mark.parametrize("T", [ON_GRID, OFF_GRID, WEEKLY, [1.0], [0.5, 1.0, 1.5]],
+                         ids=["monthly", "offgrid", "weekly", "single", "three"])
+@pytest.mark.parametrize("J", [66, 33, 16])
+def test_heston_paths_match_oracle(path, T, J, engine, best_oracle, monkeypatch):
+    monkeypatch.setenv("FOP_COS_PATH", path)
+    P = 37                                        # ragged: not a multiple of the 64-row tile
+    prm = CASES.heston_batch(P)
+    K = _strikes(J)
+    for kind in (0, 1):                           # call / put price
+        got = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.03, T, 256, kind)
+        ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.03, T, 256, kind)
+        assert_parity(got, ref, what=f"{path} path, kind {kind}, M={len(T)}, J={J}")
+
+
+@pytest.mark.parametrize("path", ["split", "fused"])
+@pytest.mark.parametrize("model", ["merton", "cgmy", "merton_cir", "cgmy_cir_diffusion", "gauss_det_clock"])
+def test_model_families_both_paths(path, model, engine, best_oracle, monkeypatch):
+    monkeypatch.setenv("FOP_COS_PATH", path)
+    K = _strikes(40)
+    T = [0.25, 0.5, 1.0, 2.0]
+    cir = [1.2, 0.8, -0.4, 1.1]
+    if model == "merton":
+        base, tc, prm = CASES.MERTON, CASES.TC_NONE, CASES.merton_batch(9)
+    elif model == "cgmy":
+        base, tc, prm = CASES.CGMY, CASES.TC_NONE, CASES.cgmy_batch(9)
+    elif model == "merton_cir":
+        base, tc = CASES.MERTON, CASES.TC_CIR
+        prm = np.hstack([CASES.merton_batch(9), np.tile(cir, (9, 1))])
+    elif model == "cgmy_cir_diffusion":
+        base, tc = CASES.CGMY, CASES.TC_CIR_DIFFUSION
+        prm = np.hstack([CASES.cgmy_batch(9), np.tile(cir, (9, 1))])
+    else:  # adaV = 0: deterministic clock branch (test.cpp:1187)
+        base, tc = CASES.GAUSS, CASES.TC_CIR
+        prm = np.array([[0.3, 1.5, 0.0, -0.5, 1.0], [0.2, 0.7, 0.0, 0.3, 0.8]])
+    got = engine.cos(base, tc, prm, K, 100.0, 0.02, T, 128, 0)
+    ref = best_oracle.cos(base, tc, prm, K, 100.0, 0.02, T, 128, 0)
+    assert_parity(got, ref, what=f"{path} path, {model}")
+
+
+@pytest.mark.parametrize("path", ["split", "fused"])
+def test_loss_and_greeks_both_paths(path, engine, best_oracle, monkeypatch):
+    monkeypatch.setenv("FOP_COS_PATH", path)
+    P = 21
+    prm = CASES.heston_batch(P)
+    K, T, w = CASES.c5_strikes(), CASES.C5_T, CASES.c5_weights()
+    mkt = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm[:1], K, 100.0, 0.0, T, 256, 0)[0]
+    got, prices = engine.cos_loss(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.0, T, 256, mkt, w,
+                                  want_prices=True)
+    ref = best_oracle.cos_loss(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.0, T, 256, mkt, w)
+    assert_parity(got, ref, what=f"{path} path fused loss")
+    assert_parity(prices, best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.0, T, 256, 0),
+                  what=f"{path} path prices next to the loss")
+    for kind in range(8):                         # every reference entry point (price/delta/gamma/theta)
+        g = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 256, kind)
+        r = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 256, kind)
+        assert_parity(g, r, what=f"{path} path kind {kind}")
+
+
+def test_paths_agree_at_bench_size(engine, monkeypatch):
+    """Full config-5 shard slice: the two paths agree with each other to rounding, and the loss is
+    reproducible run to run (fixed summation order)."""
+    import torch
+    P = 20000
+    dev = torch.device("cuda:0")
+    prm = torch.tensor(CASES.heston_batch(P), device=dev)
+    K, T = CASES.c5_strikes(), CASES.C5_T
+    outs = {}
+    for path in ("split", "fused"):
+        monkeypatch.setenv("FOP_COS_PATH", path)
+        out = torch.empty((P, 8, 66), dtype=torch.float64, device=dev)
+        engine.cos(0, 1, prm, K, 100.0, 0.0, T, 256, 0, out=out)
+        engine.synchronize()
+        outs[path] = out.cpu().numpy()
+    assert np.all(np.isfinite(outs["split"]))
+    err = np.abs(outs["split"] - outs["fused"])
+    assert np.all(err <= 1e-9 + 1e-11 * np.abs(outs["split"])), err.max()
