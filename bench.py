@@ -73,24 +73,79 @@ def market_and_weights(K, T):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    """SM clock / throttle reasons of one GPU sampled DURING the timed regions: an NVML polling
+    thread (every ~2 ms; the timed region of a short run lasts only tens of ms), falling back to
+    `nvidia-smi -lms` when NVML cannot be loaded."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, gpu_index, uuid=None):
+        import threading
+        self.sm, self.mx, self.reasons, self.power = [], [], set(), []
+        self.stop_flag = False
+        self.thread = None
+        self.p = None
+        self.mode = None
         try:
-            self.p = subprocess.Popen(
-                ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                stderr=subprocess.DEVNULL)
+            import pynvml as N
+            N.nvmlInit()
+            h = None
+            if uuid:
+                try:
+                    h = N.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = N.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.N, self.h = N, h
+            self.mx.append(float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)))
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
         except Exception:
-            self.p = None
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            try:
+                self.p = subprocess.Popen(
+                    ["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                     "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
+                    stderr=subprocess.DEVNULL)
+                self.mode = "nvidia-smi"
+            except Exception:
+                self.p = None
+
+    def _poll(self):
+        N, h = self.N, self.h
+        bits = {"hw_slowdown": getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(N, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+                self.power.append(N.nvmlDeviceGetPowerUsage(h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.mode}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=float(max(self.mx)),
+                           samples=len(self.sm), sm_min_mhz=float(min(self.sm)),
+                           power_w_max=float(max(self.power)) if self.power else None)
+            out["reasons"] = sorted(self.reasons)
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -124,21 +179,29 @@ class ClockSampler:
         return out
 
 
-def load_ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu summary (or None)."""
-    # `ncu --set full` capture of this very command (profiles/README.md), per launch
+def load_ncu_summary():
+    """Per-launch figures of the two hot kernels from the committed `ncu --set full` capture of this
+    very command (profiles/README.md): DRAM bytes per launch, and for the coefficient kernel the
+    executed fp64 operations per characteristic-function evaluation.  {} when absent."""
     path = os.path.join(ROOT, "profiles", "r1_bench_top_kernels_ncu.json")
+    out = {}
+
+    def num(s):
+        v, u = (s.split() + [""])[:2]
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(u, 1)
     try:
         for k in json.load(open(path)):
-            if "cos_gemm" in k["kernel"]:
-                def mb(s):
-                    v, u = s.split()[:2]
-                    return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
-                return {"bytes": mb(k["dram__bytes_read.sum"]) + mb(k["dram__bytes_write.sum"]),
-                        "rows": k.get("rows")}
+            name = "cos_gemm_kernel" if "cos_gemm" in k["kernel"] else \
+                "cos_coeff_kernel" if "cos_coeff" in k["kernel"] else None
+            if not name:
+                continue
+            e = {"dram_bytes": num(k["dram__bytes_read.sum"]) + num(k["dram__bytes_write.sum"])}
+            if "fp64_flops_per_cf_eval" in k:
+                e["fp64_flops_per_cf_eval"] = float(k["fp64_flops_per_cf_eval"])
+            out[name] = e
     except Exception:
         pass
-    return None
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,7 +326,7 @@ def run_ours(args):
             step_device()
         barrier()
         # ---- timed region: device-resident inputs
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local, str(getattr(torch.cuda.get_device_properties(local), 'uuid', '') or '')) if rank == 0 else None
         l0 = eng.launch_count
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -275,7 +338,6 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = eng.launch_count - l0
-        clocks = sampler.stop() if sampler else None
 
         # ---- end to end through the C ABI with host buffers
         for _ in range(2):
@@ -288,6 +350,7 @@ def run_ours(args):
                 dist.all_gather_into_tensor(gathered, loss_host.to(dev, non_blocking=True))
         barrier()
         e2e_s = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None   # sampled over both timed regions
 
         # ---- per-kernel timing for the roofline (separate pass so events do not perturb `value`)
         eng.profile_enable(True)
@@ -321,7 +384,21 @@ def run_ours(args):
         gemm_flops_per_launch = rows * J * 4.0 * NUM_U / max(gemm_n / args.steps, 1)
         gemm_avg_s = gemm_ms * 1e-3 / max(gemm_n, 1)
         achieved = gemm_flops_per_launch / gemm_avg_s / 1e12 if gemm_n else None
-        traffic = load_ncu_traffic()
+        ncu = load_ncu_summary()
+        gemm_traffic = ncu.get("cos_gemm_kernel", {}).get("dram_bytes")
+        step_kernel_ms = max(sum(v[0] for v in prof.values()), 1e-9)
+        tensor_note = ("fp64 pipe, 64 FMA/clk/SM: mma.sync.m8n8k4.f64 (DMMA) and DFMA share it; "
+                       "tcgen05/TMEM have no f64 kind")
+        peak_note = ("fp64 throughput measured live in this process (fop_microbench_fp64: DFMA %.1f, "
+                     "DMMA m8n8k4 %.1f TFLOP/s); MEASURED_PEAKS.json has no fp64 entry"
+                     % (peaks[0], peaks[1]))
+        # second hot kernel: CF evaluation has no algorithmic flop count in SURVEY 8d (reported as
+        # cf_evals); its fraction is executed fp64 flops (ncu instruction counts per evaluation,
+        # committed under profiles/) over the same measured peak
+        evals_per_step = P * M * NUM_U
+        coef_flops = ncu.get("cos_coeff_kernel", {}).get("fp64_flops_per_cf_eval")
+        coef_ach = (coef_flops * evals_per_step * args.steps / (coef_ms * 1e-3) / 1e12
+                    if coef_flops and coef_n else None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -334,16 +411,32 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "bound": "fp64", "kernel": "cos_gemm_kernel", "achieved": achieved, "peak": peak,
+                "bound": "tensor", "pipe": tensor_note, "kernel": "cos_gemm_kernel",
+                "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic["bytes"] if traffic else None,
-                "peak_source": "fp64 FMA/DMMA throughput measured live in this process "
-                               "(fop_microbench_fp64: DFMA %.1f, DMMA m8n8k4 %.1f TFLOP/s); "
-                               "MEASURED_PEAKS.json has no fp64 entry" % (peaks[0], peaks[1]),
+                "traffic": gemm_traffic,
+                "peak_source": peak_note,
                 "algorithmic_flops_per_launch": gemm_flops_per_launch,
+                "algorithmic_bytes_per_launch": rows * (2.0 * NUM_U * 8 + J * 8) / max(gemm_n / args.steps, 1),
                 "avg_launch_ms": gemm_avg_s * 1e3,
-                "share_of_step": gemm_ms / max(gemm_ms + coef_ms, 1e-9),
+                "share_of_step": gemm_ms / step_kernel_ms,
             },
+            "roofline_other": [
+                {"kernel": "cos_coeff_kernel", "bound": "tensor", "pipe": "fp64 pipe (DFMA/DMUL/DADD)",
+                 "achieved": coef_ach, "peak": peak, "unit": "TFLOP/s",
+                 "frac": (coef_ach / peak) if coef_ach else None,
+                 "what": "executed fp64 flops per CF evaluation (ncu, profiles/) x evaluations / s; "
+                         "SURVEY 8d counts no algorithmic flops for CF evaluation",
+                 "fp64_flops_per_cf_eval": coef_flops,
+                 "avg_launch_ms": coef_ms / max(coef_n, 1), "share_of_step": coef_ms / step_kernel_ms,
+                 "traffic": ncu.get("cos_coeff_kernel", {}).get("dram_bytes")},
+                {"kernel": "whole step", "bound": "tensor",
+                 "achieved": rows * J * 4.0 * NUM_U / (ms / args.steps * 1e-3) / 1e12, "peak": peak,
+                 "unit": "TFLOP/s",
+                 "frac": rows * J * 4.0 * NUM_U / (ms / args.steps * 1e-3) / 1e12 / peak,
+                 "what": "SURVEY 8d algorithmic flops (4 numU per evaluated price, CF evaluation "
+                         "not counted) over the whole step time"},
+            ],
             "kernels": {
                 k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                 for k, v in prof.items()},

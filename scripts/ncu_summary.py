@@ -41,3 +41,42 @@ if __name__ == '__main__':
         json.dump(res, open(sys.argv[2], 'w'), indent=1)
     for d in res:
         print(json.dumps(d, indent=1))
+
+
+def opcode_mix(rep, kernel_regex=None):
+    """Executed-instruction mix per kernel from the source page (SASS): warp instructions by
+    opcode, the fp64 flop count (2 per DFMA thread instruction, 1 per DMUL / DADD) and the stall
+    samples by opcode."""
+    import collections
+    import re
+    cmd = ['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass']
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
+    res, cur = [], None
+    for row in csv.reader(out.splitlines()):
+        if row and row[0] == 'Kernel Name':
+            cur = {'kernel': row[1], 'rows': []}
+            res.append(cur)
+        elif row and row[0] == 'Address':
+            cur['hdr'] = row
+        elif cur is not None and 'hdr' in cur and len(row) == len(cur['hdr']):
+            cur['rows'].append(row)
+    summ = []
+    for k in res:
+        if kernel_regex and not re.search(kernel_regex, k['kernel']):
+            continue
+        ix = {h: i for i, h in enumerate(k['hdr'])}
+        ex, th, sm = collections.Counter(), collections.Counter(), collections.Counter()
+        for r in k['rows']:
+            parts = r[ix['Source']].split()
+            op = (parts[1] if parts[0].startswith('@') else parts[0]).split('.')[0]
+            ex[op] += int(r[ix['Instructions Executed']])
+            th[op] += int(r[ix['Predicated-On Thread Instructions Executed']])
+            sm[op] += int(r[ix['# Samples']])
+        tot = sum(ex.values())
+        summ.append({'kernel': k['kernel'], 'warp_instructions': tot,
+                     'fp64_flops': 2 * th['DFMA'] + th['DMUL'] + th['DADD'],
+                     'fp64_warp_instructions': ex['DFMA'] + ex['DMUL'] + ex['DADD'] + ex['DSETP'],
+                     'mix_pct': {o: round(100.0 * n / tot, 2) for o, n in ex.most_common(16)},
+                     'stall_samples_pct': {o: round(100.0 * n / max(sum(sm.values()), 1), 2)
+                                           for o, n in sm.most_common(10)}})
+    return summ
