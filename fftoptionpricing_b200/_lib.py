@@ -58,6 +58,8 @@ _SIGNATURES = {
     "fop_fo_estimate": (C.c_int, [_dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_int, _dp, C.c_int, _dp]),
     "fop_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
+    "fop_integrate_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                    C.c_double, C.c_int, C.c_void_p]),
     "fop_measure_fp64_peak": (C.c_int, [C.c_void_p, _dp]),
 }
 # not part of the public header: tuning probe used by profiles/ scripts

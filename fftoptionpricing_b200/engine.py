@@ -232,6 +232,27 @@ class Engine:
                                     int(bool(inverse))))
         return z
 
+    def integrate_fft(self, fn_samples, outputMin, inputMin, inputMax, inverse=False, out=None):
+        """integrateFFT / integrateIFFT (fft.hpp:96-110) of functions given by their samples on the
+        uniform input grid, batched over the leading axes.  numpy in -> numpy out; a torch CUDA
+        complex128 tensor in -> torch tensor out (``out`` may be the input)."""
+        if _is_torch(fn_samples):
+            import torch
+            N = fn_samples.shape[-1]
+            o = out if out is not None else torch.empty_like(fn_samples)
+            ib, ob = _Buf(fn_samples, dtype=np.complex128), _Buf(o, dtype=np.complex128)
+            self._check(self._L.fop_integrate_fft(self._h, ib.ptr, fn_samples.numel() // N, N,
+                                                  float(outputMin), float(inputMin), float(inputMax),
+                                                  int(bool(inverse)), ob.ptr))
+            return o
+        z = np.ascontiguousarray(np.asarray(fn_samples, dtype=np.complex128))
+        N = z.shape[-1]
+        o = np.empty_like(z)
+        self._check(self._L.fop_integrate_fft(self._h, C.c_void_p(z.ctypes.data), z.size // N, N,
+                                              float(outputMin), float(inputMin), float(inputMax),
+                                              int(bool(inverse)), C.c_void_p(o.ctypes.data)))
+        return o
+
     # ------------------------------------------------------------------ grids (host)
     def carr_madan_strikes(self, N, ada, S0):
         out = np.empty(N)

@@ -198,6 +198,20 @@ int fop_fo_estimate(const double* strikes, const double* options, int n, double 
  */
 int fop_fft(fop_handle_t h, double* data, int batch, int N, int inverse);
 
+/* ---- integrateFFT / integrateIFFT  (fft.hpp:64-110, genericIntegration) -----------------------
+ * Simpson-weighted Fourier integral of a function sampled on a uniform grid:
+ *   inputDx = (inputMax - inputMin)/(N-1),  du = ((N-1) 2 pi/(inputMax - inputMin))/N
+ *   x_j   = fn_j inputDx e^{i outputMin inputDx j}/3 * {1 at j = 0, N-1; 2 (j even); 4 (j odd)}
+ *   X     = fft(x) (inverse = 0, integrateFFT) or ifft(x) (inverse = 1, integrateIFFT), unnormalised
+ *   out_m = X_m e^{i u_m inputMin},  u_m = outputMin + m du
+ * fn_samples[batch][N] complex128 = the reference's callable `fn` evaluated by the caller at
+ * inputMin + inputDx j (a device function cannot be an arbitrary host callable); out[batch][N]
+ * complex128 (may alias fn_samples).  The reference's optional `fnOutput(u, v)` edit is applied by
+ * the caller to out.  N power of two, 16 <= N <= 2^20.
+ */
+int fop_integrate_fft(fop_handle_t h, const double* fn_samples, int batch, int N, double outputMin,
+                      double inputMin, double inputMax, int inverse, double* out);
+
 /* measured fp64 FMA throughput of the device in TFLOP/s (roofline denominator, bench.py) */
 int fop_measure_fp64_peak(fop_handle_t h, double* tflops_out);
 

@@ -60,6 +60,7 @@ class Oracle:
         L.ora_objfn_cf.argtypes = [i, i, _dp, i, _dp, _dp, i, d, d, _dp]
         L.ora_cos_loss.argtypes = [i, i, _dp, i, _dp, i, d, d, _dp, i, i, _dp, _dp, _dp, _dp]
         L.ora_fft.argtypes = [_dp, i, i, i]
+        L.ora_integrate_fft.argtypes = [_dp, i, i, d, d, d, i, _dp]
         L.ora_cf.argtypes = [i, i, _dp, d, d, d, d, _dp, _dp]
         L.ora_fo_estimate.argtypes = [_dp, _dp, i, d, d, d, d, d, i, _dp, i, _dp]
         L.ora_carr_madan_strikes.argtypes = [i, d, d, _dp]
@@ -138,6 +139,17 @@ class Oracle:
         flat = z2.view(np.float64)
         self._check(self.lib.ora_fft(_ptr(flat), z2.shape[0], shape[-1], int(inverse)), "fft")
         return z2.reshape(shape)
+
+    def integrate_fft(self, fn_samples, outputMin, inputMin, inputMax, inverse=False):
+        z = np.ascontiguousarray(np.asarray(fn_samples, dtype=np.complex128))
+        shape = z.shape
+        z2 = z.reshape(-1, shape[-1])
+        out = np.empty_like(z2)
+        self._check(self.lib.ora_integrate_fft(_ptr(z2.view(np.float64)), z2.shape[0], shape[-1],
+                                               float(outputMin), float(inputMin), float(inputMax),
+                                               int(inverse), _ptr(out.view(np.float64))),
+                    "integrate_fft")
+        return out.reshape(shape)
 
     def cf(self, base, tc, params, r, T, u: complex):
         p = _arr(params)

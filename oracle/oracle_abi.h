@@ -33,6 +33,10 @@ int ora_cos_loss(int base, int tc, const double* params, int P, const double* K_
                  const double* w, double* loss, double* prices_out);
 /* reference radix-2 FFT (fft.hpp:49-61), in place, `batch` sequences of N interleaved complex */
 int ora_fft(double* data, int batch, int N, int inverse);
+/* integrateFFT / integrateIFFT (fft.hpp:64-110) of a function given by its N samples on the input
+ * grid (the callable handed to the reference looks the sample up by index) */
+int ora_integrate_fft(const double* fn_samples, int batch, int N, double outputMin, double inputMin,
+                      double inputMax, int inverse, double* out);
 /* CF value phi(u) and log-CF at u = (u_re, u_im) for one parameter set (unit tests of the CF lib) */
 int ora_cf(int base, int tc, const double* params, double r, double T, double u_re, double u_im,
            double* cf_out2, double* logcf_out2);

@@ -291,6 +291,31 @@ int ora_fft(double* data, int batch, int N, int inverse) {
   return 0;
 }
 
+// restatement of genericIntegration (fft.hpp:64-82)
+int ora_integrate_fft(const double* fn_samples, int batch, int N, double outputMin, double inputMin,
+                      double inputMax, int inverse, double* out) {
+  if (!fn_samples || !out || N < 2 || (N & (N - 1)) || !(inputMax > inputMin)) return 1;
+  const double range = inputMax - inputMin, inputDx = range / (N - 1);
+  const double outputMax = outputMin + (N - 1) * 2.0 * M_PI / range, du = (outputMax - outputMin) / N;
+  const cplx I(0.0, 1.0);
+  for (int b = 0; b < batch; ++b) {
+    const double* f = fn_samples + (size_t)b * 2 * N;
+    std::vector<cplx> x(N);
+    for (int j = 0; j < N; ++j) {
+      const cplx v = cplx(f[2 * j], f[2 * j + 1]) * inputDx * std::exp(outputMin * inputDx * j * I) / 3.0;
+      x[j] = (j == 0 || j == N - 1) ? v : (j % 2 == 0 ? 2.0 * v : 4.0 * v);
+    }
+    if (inverse) inv(x); else fwd(x);
+    double* o = out + (size_t)b * 2 * N;
+    for (int j = 0; j < N; ++j) {
+      const double u = outputMin + j * du;
+      const cplx r = x[j] * std::exp(u * inputMin * I);
+      o[2 * j] = r.real(); o[2 * j + 1] = r.imag();
+    }
+  }
+  return 0;
+}
+
 int ora_cf(int base, int tc, const double* params, double r, double T, double u_re, double u_im,
            double* cf_out2, double* logcf_out2) {
   if (oramodel::numParams(base, tc) == 0 || !params) return 1;

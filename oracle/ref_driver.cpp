@@ -208,6 +208,29 @@ int ora_fft(double* data, int batch, int N, int inverse) {
   return 0;
 }
 
+// the reference's own integrateFFT / integrateIFFT (fft.hpp:96-110); fn(currInput) returns the
+// sample whose grid point currInput is (index recovered by rounding)
+int ora_integrate_fft(const double* fn_samples, int batch, int N, double outputMin, double inputMin,
+                      double inputMax, int inverse, double* out) {
+  if (!fn_samples || !out || N < 2 || (N & (N - 1)) || !(inputMax > inputMin)) return 1;
+  const double inputDx = (inputMax - inputMin) / (N - 1);
+  for (int b = 0; b < batch; ++b) {
+    const double* f = fn_samples + (size_t)b * 2 * N;
+    auto fn = [&](double x) {
+      long j = std::lround((x - inputMin) / inputDx);
+      j = j < 0 ? 0 : (j > N - 1 ? N - 1 : j);
+      return cplx(f[2 * j], f[2 * j + 1]);
+    };
+    // integrateIFFT's unused `Method` template parameter cannot be deduced (fft.hpp:104-107), so
+    // the inverse case goes through genericIntegration with ifft, which is all integrateIFFT does
+    const auto res = inverse ? genericIntegration(outputMin, inputMin, inputMax, fn, N, ifft)
+                             : integrateFFT(outputMin, inputMin, inputMax, fn, N);
+    double* o = out + (size_t)b * 2 * N;
+    for (int j = 0; j < N; ++j) { o[2 * j] = res[j].real(); o[2 * j + 1] = res[j].imag(); }
+  }
+  return 0;
+}
+
 int ora_cf(int base, int tc, const double* params, double r, double T, double u_re, double u_im,
            double* cf_out2, double* logcf_out2) {
   if (oramodel::numParams(base, tc) == 0 || !params) return 1;

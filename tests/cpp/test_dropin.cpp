@@ -7,6 +7,7 @@
 
 #include "fftop/OptionCalibration.h"
 #include "fftop/OptionPricing.h"
+#include "fftop/fft.h"
 
 static int failures = 0;
 // Catch v1 Approx semantics: |a-b| < eps (1 + max(|a|,|b|))
@@ -72,6 +73,28 @@ int main() {
     auto hoc = optioncal::getObjFn_arr(std::move(ph), fftop::blackScholes(.3), std::move(u), 0.0, 1.0);
     std::vector<double> bad = {std::nan("")};
     REQUIRE_APPROX(hoc(bad), 5000.0, 1e-15);
+  }
+  {  // fft.h drop-in: ifft(fft(x)) = N x (fft.hpp:1-4: no 1/N either way) and integrateFFT of a
+     // normal density = its characteristic function (frequency -m du inside the sum, fft.hpp:70-81)
+    const int N = 1024;
+    CArray x(N);
+    for (int i = 0; i < N; ++i) x[i] = Complex(std::sin(0.1 * i), std::cos(0.3 * i));
+    CArray y = ifft(fft(CArray(x)));
+    for (int i = 0; i < N; i += 37) {
+      REQUIRE_APPROX(y[i].real() / N, x[i].real(), 1e-12);
+      REQUIRE_APPROX(y[i].imag() / N, x[i].imag(), 1e-12);
+    }
+    const double lo = -8.0, hi = 8.0, mu = .3, sg = .8;
+    auto dens = [&](double t) { return Complex(std::exp(-.5 * (t - mu) * (t - mu) / (sg * sg)) / (sg * std::sqrt(2 * M_PI)), 0.0); };
+    CArray f = integrateFFT(0.0, lo, hi, dens, 4096);
+    const double du = ((4096 - 1) * 2.0 * M_PI / (hi - lo)) / 4096;
+    for (int m = 0; m < 30; m += 7) {
+      const double v = -m * du;
+      const Complex expect = std::exp(Complex(-.5 * sg * sg * v * v, v * mu)) * std::exp(Complex(0.0, -v * lo)) *
+                             std::exp(Complex(0.0, m * du * lo));
+      REQUIRE_APPROX(f[m].real(), expect.real(), 1e-9);
+      REQUIRE_APPROX(f[m].imag(), expect.imag(), 1e-9);
+    }
   }
   std::printf(failures ? "FAILED %d\n" : "ALL PASSED\n", failures);
   return failures != 0;
