@@ -4,13 +4,12 @@
 #include <algorithm>
 #include <cmath>
 
-#include "cf_models.cuh"
 #include "handle.cuh"
+#include "objfn_common.cuh"
 
 namespace {
 using namespace fop;
 
-constexpr double kLargeNumber = 5000.0;  // OptionCalibration.h:185
 constexpr int OBJ_WARPS = 8;
 
 struct ObjArgs {
@@ -30,24 +29,9 @@ __global__ void __launch_bounds__(32 * OBJ_WARPS) objfn_cf_kernel(const ObjArgs 
   ModelConsts* consts = reinterpret_cast<ModelConsts*>(smem_raw);
   double* terms = reinterpret_cast<double*>(smem_raw + sizeof(ModelConsts) * OBJ_WARPS) + (size_t)warp * a.m;
   for (int p = blockIdx.x * OBJ_WARPS + warp; p < a.P; p += gridDim.x * OBJ_WARPS) {
-    if (lane == 0) make_consts(a.base, a.tc, a.params + (size_t)p * a.np, consts[warp]);
-    __syncwarp();
-    const ModelConsts& mc = consts[warp];
-    for (int l = lane; l < a.m; l += 32) {
-      const cd u = mk(1.0, __ldg(a.u + l));
-      CfPre pre;
-      cf_prepare(a.base, a.tc, mc, u, a.r, pre);
-      const cd c = cf_log_at(a.tc, mc, pre, a.T);
-      const double dr = __ldg(a.phiHat + 2 * l) - c.x, di = __ldg(a.phiHat + 2 * l + 1) - c.y;
-      terms[l] = (isnan(c.x) || isnan(c.y)) ? kLargeNumber : dr * dr + di * di;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      double acc = 0.0;
-      for (int l = 0; l < a.m; ++l) acc += terms[l];
-      a.loss[p] = acc / (double)a.m;
-    }
-    __syncwarp();
+    const double v = warp_objfn_cf(a.base, a.tc, a.params + (size_t)p * a.np, a.m, a.u, a.phiHat, a.r,
+                                   a.T, consts[warp], terms);
+    if (lane == 0) a.loss[p] = v;
   }
 }
 

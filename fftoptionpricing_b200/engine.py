@@ -202,6 +202,29 @@ class Engine:
                                          phb.ptr, ub.size, float(r), float(T), ob.ptr))
         return out
 
+    def calibrate_cf(self, base, tc, lower, upper, u, phiHat, r, T, nests=25, iterations=1500,
+                     tol=1e-12, seed=42, restarts=1):
+        """On-device cuckoo search over the objective of ``objfn_cf`` (replaces the reference's
+        cuckoo::optimize call, generateCharts.cpp:115).  Returns ``(params[restarts, np],
+        fnval[restarts], iterations[restarts], best_restart)``."""
+        npar = num_params(base, tc)
+        lo = np.ascontiguousarray(np.asarray(lower, dtype=np.float64))
+        hi = np.ascontiguousarray(np.asarray(upper, dtype=np.float64))
+        assert lo.size == npar and hi.size == npar, (lo.size, hi.size, npar)
+        ub = _Buf(u)
+        ph = np.ascontiguousarray(np.asarray(phiHat, dtype=np.complex128))
+        assert ph.size == ub.size
+        prm = np.empty((restarts, npar))
+        fv = np.empty(restarts)
+        its = np.empty(restarts, dtype=np.int32)
+        best = C.c_int(0)
+        self._check(self._L.fop_calibrate_cf(
+            self._h, _lib.fop_model_t(base, tc), lo.ctypes.data_as(_lib._dp), hi.ctypes.data_as(_lib._dp),
+            ub.ptr, C.c_void_p(ph.ctypes.data), ub.size, float(r), float(T), int(nests),
+            int(iterations), float(tol), int(seed), int(restarts), C.c_void_p(prm.ctypes.data),
+            C.c_void_p(fv.ctypes.data), C.c_void_p(its.ctypes.data), C.byref(best)))
+        return prm, fv, its, best.value
+
     def cos_loss(self, base, tc, params, K_desc, S0, r, T, numU, mkt, w=None, want_prices=False,
                  out=None, prices_out=None):
         pb, P = self._params(base, tc, params)

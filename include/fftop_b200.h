@@ -190,6 +190,23 @@ int fop_fo_estimate(const double* strikes, const double* options, int n, double 
                     double t, double minStrike, double maxStrike, int N, const double* u, int m,
                     double* phiHat_out);
 
+/* ---- on-device calibration of the CF-space objective -------------------------------------------
+ * Replaces the reference's cuckoo::optimize(objFn, constraints, nestSize, numSims, tol, seed) over
+ * the closure of getObjFn_arr (generateCharts.cpp:102-118; library cuckoo_search is un-vendored):
+ * cuckoo search (Levy flights + abandonment, greedy acceptance) with `nests` nests for at most
+ * `iterations` iterations or until the best objective value drops below `tol`, inside one kernel
+ * launch.  `restarts` independent searches (seeded streams `seed`, restart index) run as one CTA
+ * each -- use a multiple of the SM count to fill the GPU; restart 0 alone is the reference's
+ * single search.  lower/upper[np]: box constraints (swarm_utils::upper_lower).
+ * Outputs (host or device): params_out[restarts][np], fnval_out[restarts], iters_out[restarts]
+ * (optional), *best_restart_out = argmin fnval (host int, optional).  fnval_out[i] is bit-identical
+ * to fop_objfn_cf evaluated at params_out[i].  2 <= nests <= 64, 1 <= m <= 2048.
+ */
+int fop_calibrate_cf(fop_handle_t h, fop_model_t model, const double* lower, const double* upper,
+                     const double* u, const double* phiHat, int m, double r, double T, int nests,
+                     int iterations, double tol, unsigned long long seed, int restarts,
+                     double* params_out, double* fnval_out, int* iters_out, int* best_restart_out);
+
 /* ---- batched FFT (the replacement for fft.hpp:49-61; exposed for parity tests) ---------------
  * In-place unnormalised transforms of `batch` contiguous length-N complex128 sequences
  * (interleaved re,im -- the layout of the reference's CArray, fft.h:12-13).

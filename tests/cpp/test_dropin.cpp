@@ -7,6 +7,7 @@
 
 #include "fftop/OptionCalibration.h"
 #include "fftop/OptionPricing.h"
+#include "fftop/cuckoo.h"
 #include "fftop/fft.h"
 
 static int failures = 0;
@@ -73,6 +74,21 @@ int main() {
     auto hoc = optioncal::getObjFn_arr(std::move(ph), fftop::blackScholes(.3), std::move(u), 0.0, 1.0);
     std::vector<double> bad = {std::nan("")};
     REQUIRE_APPROX(hoc(bad), 5000.0, 1e-15);
+  }
+  {  // cuckoo::optimize call shape of generateCharts.cpp:102-118 (BS: one parameter, target sigma = .3)
+    std::vector<double> u = {-15, -10, -5, 5, 10, 15};
+    std::vector<std::complex<double>> ph;
+    for (double ul : u) {  // log CF of BS at 1 + i u: (1+iu)(r - s^2/2) T + s^2 (1+iu)^2 T / 2, r = 0, T = 1
+      const std::complex<double> z(1.0, ul);
+      ph.push_back(z * (-.045) + .045 * z * z);
+    }
+    auto objFn = optioncal::getObjFn_arr(std::move(ph), fftop::blackScholes(.3), std::move(u), 0.0, 1.0);
+    std::vector<swarm_utils::upper_lower<double>> constraints = {swarm_utils::upper_lower<double>(0.0, .6)};
+    const auto results = cuckoo::optimize(objFn, constraints, 25, 300, 1e-20, 42);
+    auto params = std::get<swarm_utils::optparms>(results);
+    auto objFnRes = std::get<swarm_utils::fnval>(results);
+    REQUIRE_APPROX(params[0], .3, 1e-4);
+    REQUIRE_APPROX(objFnRes, objFn(params), 1e-15);
   }
   {  // fft.h drop-in: ifft(fft(x)) = N x (fft.hpp:1-4: no 1/N either way) and integrateFFT of a
      // normal density = its characteristic function (frequency -m du inside the sum, fft.hpp:70-81)
