@@ -205,9 +205,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M * lossblk) : nullptr;
   double* d_loss = loss ? (loss_host ? ar.alloc<double>(P) : loss) : nullptr;
 
-  // few strike blocks (epilogue-heavy, e.g. 66 strikes): the 16-row warp tile measured 5 % faster;
-  // many strike blocks (1024 strikes): the 32-row tile measured 2 % faster
-  const int mb = nblk <= 2 ? 2 : 4;
+  // 32-row warp tiles (4 warps per CTA) measure 1-2 % faster than 16-row tiles (8 warps) for both
+  // 66 and 1024 strikes since the epilogue runs from registers; FOP_GEMM_MB=2 selects the latter
+  int mb = 4;
+  if (const char* e = std::getenv("FOP_GEMM_MB")) mb = atoi(e) == 2 ? 2 : 4;
   auto gemm_kernel = mb == 2 ? gv->dmma2 : gv->dmma4;
   const size_t gemm_smem = cos_dmma_smem(gv->NB);
   FOP_CUDA(h, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
@@ -270,6 +271,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ga.C = d_C + (size_t)plane_of[kind >> 1] * rows * KK;
       ga.basis = d_basis;  ga.T = d_T;  ga.strikes = d_K;
       ga.out = out ? (out_host ? d_out_tmp : out_k) : nullptr;
+      ga.vec2 = (J % 2 == 0) && (JB % 2 == 0) && (reinterpret_cast<uintptr_t>(ga.out) % 16 == 0);
       ga.mkt = d_mkt;  ga.w = d_w;
       ga.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
       const dim3 ggrid((unsigned)((rows + DM_RT - 1) / DM_RT), (unsigned)nblk);

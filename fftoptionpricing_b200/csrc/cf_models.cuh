@@ -157,8 +157,9 @@ __device__ __forceinline__ cx<T> cf_log_cir_given_e(const ModelConsts& c, const 
                                                     cx<T> l, cx<T> e) {
   const cx<T> ome = 1.0 - e;
   const cx<T> w = 1.0 - pre.g * ome;
-  const cx<T> b = pre.pod * cdiv(ome, w);
-  const cx<T> lw = clog(w);
+  cx<T> q, lw;
+  cdiv_clog_unit(ome, w, &q, &lw);
+  const cx<T> b = pre.pod * q;
   const cx<T> cc = mk(c.aos2 * (2.0 * lw.x + pre.dmk.x * Tm), c.aos2 * (2.0 * lw.y + pre.dmk.y * Tm));
   return l - (c.v0 * b) - cc;
 }

@@ -101,8 +101,8 @@ __device__ __forceinline__ void coeff_maturities(const CosCoeffArgs& a, const Mo
   for (; m < M; ++m) coeff_group<MODE, 1>(a, mc, pre, E, u, v, crow, Kp, m);
 }
 
-template <int ILP>
-__global__ void __launch_bounds__(256, 2) cos_coeff_kernel(const CosCoeffArgs a) {
+template <int ILP, int NT = 256, int MINB = 2>
+__global__ void __launch_bounds__(NT, MINB) cos_coeff_kernel(const CosCoeffArgs a) {
   __shared__ ModelConsts consts[COEFF_MAX_SPB];
   const int tid = threadIdx.x;
   const int K = a.K, M = a.M;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256, 2) cos_coeff_kernel(const CosCoeffArgs a)
     if (tid < nsets) make_consts(a.base, a.tc, a.params + (size_t)(p0 + tid) * a.np, consts[tid]);
     __syncthreads();
     const int Kp = a.Kp;
-    for (int idx = tid; idx < nsets * Kp; idx += 256) {
+    for (int idx = tid; idx < nsets * Kp; idx += NT) {
       const int s = idx / Kp, k = idx - s * Kp;
       double2* crow = reinterpret_cast<double2*>(a.C) + (size_t)(p0 + s) * M * Kp + k;
       if (k >= K) {  // zero padding so the contraction can run full stages
@@ -153,6 +153,7 @@ struct CosGemmArgs {
   const double* mkt;      // [M][J] or nullptr
   const double* w;        // [M][J] or nullptr
   double* rowloss;        // [rows][nblk] or nullptr
+  int vec2;               // prices may be stored as 16-byte pairs (J even, out 16-byte aligned)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -177,8 +178,7 @@ constexpr int DM_AS = DM_KC + 4;     // A row stride (288 B: rows shift by 32 B 
 __host__ __device__ constexpr int dm_bs(int NB) { return 8 * NB + 4; }  // B row stride (doubles)
 __host__ __device__ inline size_t cos_dmma_smem(int NB) {
   const size_t stage = (size_t)DM_RT * DM_AS * 8 + (size_t)DM_KC * dm_bs(NB) * 8;
-  const size_t epi = (size_t)DM_RT * (8 * NB + 2) * 8;
-  return 2 * stage > epi ? 2 * stage : epi;
+  return 2 * stage;
 }
 
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
@@ -211,7 +211,7 @@ __host__ __device__ inline CosEpi cos_epi_consts(int kind, double S0, double r) 
 template <int NB, int MB>
 __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kernel(const CosGemmArgs a) {
   constexpr int NT = 32 * (DM_RT / (8 * MB));
-  constexpr int JB = 8 * NB, JBP = JB + 2, BS = dm_bs(NB);
+  constexpr int JB = 8 * NB, BS = dm_bs(NB);
   constexpr size_t A_BYTES = (size_t)DM_RT * DM_AS * 8;
   constexpr size_t STAGE = A_BYTES + (size_t)DM_KC * BS * 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kern
   const int KKp = a.KK;  // padded
   const int nchunks = KKp / DM_KC;
   const CosEpi epi = cos_epi_consts(a.kind, a.S0, a.r);
+  const int jvalid = min(JB, a.J - blk * JB);
 
   // cp.async plan (fully coalesced: consecutive threads copy consecutive 16-byte pieces).
   //   A: piece q = tid + NT i  ->  row (tid >> 4) + (NT/16) i, piece tid & 15 of the row's 256 B
@@ -316,42 +317,51 @@ __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kern
     __syncthreads();
   }
 
-  // ---- epilogue through shared memory: one warp per row, lanes along strikes
-  double* Es = reinterpret_cast<double*>(smem_raw);
+  // ---- epilogue straight from the accumulator fragment: the lane holds rows wrow + 8 i + g and
+  // columns 8 j + 2 c, + 1.  No shared-memory staging and no barrier: the 2 MB x NB loads / stores
+  // of a lane are independent, so their latency overlaps (the staged, row-at-a-time version spent
+  // 42 % of the warp samples waiting on its dependent load -> add -> shuffle chains,
+  // profiles/r1_bench_top_kernels_ncu.json of that revision).
+  const bool vec2 = a.vec2 != 0;
 #pragma unroll
-  for (int i = 0; i < MB; ++i)
-#pragma unroll
-    for (int j = 0; j < NB; ++j)
-      *reinterpret_cast<double2*>(Es + (size_t)(wrow + 8 * i + g) * JBP + 8 * j + 2 * c) =
-          make_double2(acc[i][j][0], acc[i][j][1]);
-  __syncthreads();
-  const int jvalid = min(JB, a.J - blk * JB);
-  constexpr int PASSES = (JB + 31) / 32;
-  for (int rr = warp; rr < nrows; rr += NT / 32) {
+  for (int i = 0; i < MB; ++i) {
+    const int rr = wrow + 8 * i + g;
+    const bool valid = rr < nrows;
     const long long row = row0 + rr;
-    const double rs = s_rowscale[rr];
-    const int m = s_rowm[rr];
-    const double* es = Es + (size_t)rr * JBP;
-    double* orow = a.out ? a.out + (size_t)row * a.J + (size_t)blk * JB : nullptr;
-    const double* mrow = a.mkt ? a.mkt + (size_t)m * a.J + (size_t)blk * JB : nullptr;
-    const double* wrw = a.w ? a.w + (size_t)m * a.J + (size_t)blk * JB : nullptr;
+    const double rs = s_rowscale[valid ? rr : 0];
+    const int m = s_rowm[valid ? rr : 0];
+    double* orow = a.out && valid ? a.out + (size_t)row * a.J + (size_t)blk * JB : nullptr;
+    const double* mrow = a.mkt && valid ? a.mkt + (size_t)m * a.J + (size_t)blk * JB : nullptr;
+    const double* wrw = a.w && valid ? a.w + (size_t)m * a.J + (size_t)blk * JB : nullptr;
     double lsum = 0.0;
 #pragma unroll
-    for (int ps = 0; ps < PASSES; ++ps) {
-      const int jj = lane + 32 * ps;
-      if (jj < jvalid) {
-        const double o = fma(es[jj] - epi.sub, rs * s_strike[jj], epi.add);
-        if (orow) orow[jj] = o;
-        if (mrow) {
-          const double d = o - __ldg(mrow + jj);
-          lsum = fma((wrw ? __ldg(wrw + jj) : 1.0) * d, d, lsum);
+    for (int j = 0; j < NB; ++j) {
+      const int j0 = 8 * j + 2 * c;
+      const double o0 = fma(acc[i][j][0] - epi.sub, rs * s_strike[j0], epi.add);
+      const double o1 = fma(acc[i][j][1] - epi.sub, rs * s_strike[j0 + 1], epi.add);
+      if (orow) {
+        if (vec2) {
+          if (j0 < jvalid) *reinterpret_cast<double2*>(orow + j0) = make_double2(o0, o1);
+        } else {
+          if (j0 < jvalid) orow[j0] = o0;
+          if (j0 + 1 < jvalid) orow[j0 + 1] = o1;
+        }
+      }
+      if (mrow) {
+        if (j0 < jvalid) {
+          const double d = o0 - __ldg(mrow + j0);
+          lsum = fma((wrw ? __ldg(wrw + j0) : 1.0) * d, d, lsum);
+        }
+        if (j0 + 1 < jvalid) {
+          const double d = o1 - __ldg(mrow + j0 + 1);
+          lsum = fma((wrw ? __ldg(wrw + j0 + 1) : 1.0) * d, d, lsum);
         }
       }
     }
-    if (a.rowloss) {
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
-      if (lane == 0) a.rowloss[(size_t)row * a.nblk + blk] = lsum;
+    if (a.rowloss) {  // fixed order: the lane's columns, then lanes c = 0..3 -> deterministic
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+      lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+      if (c == 0 && valid) a.rowloss[(size_t)row * a.nblk + blk] = lsum;
     }
   }
 }

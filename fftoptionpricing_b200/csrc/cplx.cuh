@@ -67,6 +67,15 @@ template <class T> CX_HD cx<T> clog(cx<T> z) {
   const T lr = fm_fma(fm_i2d(e), FM_TAB(fm_k)[16], 0.5 * fm_log_pos(n));
   return mk(fm_sel(big == 0.0, -(double)INFINITY, lr), fm_atan2(z.y, z.x));
 }
+// q = a / w and lw = log w in one go for |w| = O(1) (the CIR clock's w = 1 - g (1 - e), which is 1
+// at u = 0 and stays between ~1e-3 and ~10): |w|^2 is formed once, unscaled, and shared by the
+// reciprocal and the logarithm; atan2 skips its power-of-two pre-scaling.
+template <class T> CX_HD void cdiv_clog_unit(cx<T> a, cx<T> w, cx<T>* q, cx<T>* lw) {
+  const T n = fm_fma(w.x, w.x, w.y * w.y);
+  const T inv = fm_rcp(n);
+  *q = mk((a.x * w.x + a.y * w.y) * inv, (a.y * w.x - a.x * w.y) * inv);
+  *lw = mk(0.5 * fm_log_pos(n), fm_atan2_normal(w.y, w.x));
+}
 // principal square root (Re >= 0; on the negative real axis the sign of Im follows the sign of z.y)
 __device__ __forceinline__ cd csqrt(cd z) {
   if (z.x == 0.0 && z.y == 0.0) return mk(0.0, z.y);

@@ -272,18 +272,21 @@ template <class T> FM_HD T fm_log_pos(T x) {
   return fm_fma(dk, K[7], -((hfsq - fm_fma(s, hfsq + R, dk * K[8])) - f));
 }
 
-// atan2(y, x), finite arguments; (0, 0) -> 0 or pi like the C library
-template <class T> FM_HD T fm_atan2(T y, T x) {
+// atan2(y, x).  SCALE = true: any finite arguments ((0, 0) -> 0 or pi like the C library): the pair
+// is first brought into [1, 2) by a power of two (tiny -- incl. subnormal, which rcp.approx
+// flushes -- or huge operands; the ratio is unchanged).  SCALE = false: the caller guarantees
+// 1e-290 < max(|x|, |y|) < 1e290 and saves the ten instructions of that step.
+template <bool SCALE, class T> FM_HD T fm_atan2_impl(T y, T x) {
   FM_TABPTR K = FM_TAB(fm_k);
   T ax = fm_abs(x), ay = fm_abs(y);
-  // bring tiny (incl. subnormal: rcp.approx flushes them) or huge pairs into the safe range;
-  // powers of two, so the ratio is unchanged
-  const T top = fm_sel(ax > ay, ax, ay);
-  auto e = ((fm_hi(top) >> 20) & 0x7ff) - 1023;
-  e = fm_sel(e < -1020, -1020, fm_sel(e > 1020, 1020, e));
-  const T sc = fm_make((1023 - e) << 20, 0);  // 2^-e: the larger operand lands in [1, 2)
-  ax = ax * sc;
-  ay = ay * sc;
+  if (SCALE) {
+    const T top = fm_sel(ax > ay, ax, ay);
+    auto e = ((fm_hi(top) >> 20) & 0x7ff) - 1023;
+    e = fm_sel(e < -1020, -1020, fm_sel(e > 1020, 1020, e));
+    const T sc = fm_make((1023 - e) << 20, 0);  // 2^-e: the larger operand lands in [1, 2)
+    ax = ax * sc;
+    ay = ay * sc;
+  }
   const auto xbig = ax > ay;
   const T mx = fm_sel(xbig, ax, ay), mn = fm_sel(xbig, ay, ax);
   const auto big = mn > K[9] * mx;  // tan(pi/8)
@@ -303,6 +306,8 @@ template <class T> FM_HD T fm_atan2(T y, T x) {
   a = fm_sel(fm_hi(x) < 0, K[14] - (a - K[15]), a);
   return fm_make(fm_hi(a) ^ (fm_hi(y) & 0x80000000), fm_lo(a));
 }
+template <class T> FM_HD T fm_atan2(T y, T x) { return fm_atan2_impl<true>(y, x); }
+template <class T> FM_HD T fm_atan2_normal(T y, T x) { return fm_atan2_impl<false>(y, x); }
 
 #undef FM_LANES
 
