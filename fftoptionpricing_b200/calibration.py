@@ -28,7 +28,23 @@ def getObjFn_arr(phiHat, model: CF, uArray, r: float, T: float, engine: Optional
         eng = engine or default_engine()
         return eng.objfn_cf(model.base, model.time_change, params, uArray, phiHat, r, T)
 
+    objFn.model, objFn.phiHat, objFn.uArray, objFn.r, objFn.T, objFn.engine = model, phiHat, uArray, r, T, engine
     return objFn
+
+
+def cuckoo_optimize(objFn, constraints, nestSize=25, numSims=1500, tol=1e-12, seed=42, restarts=1):
+    """Mirror of the reference's ``cuckoo::optimize(objFn, constraints, nestSize, numSims, tol, seed)``
+    call (generateCharts.cpp:115) for an ``objFn`` made by :func:`getObjFn_arr`: the whole search
+    runs on the device (fop_calibrate_cf; ``restarts`` independent searches, one CTA each).
+    ``constraints``: sequence of (lower, upper).  Returns ``(params, fnval)`` of the best restart."""
+    from .pricing import default_engine
+    eng = objFn.engine or default_engine()
+    lo = [c[0] for c in constraints]
+    hi = [c[1] for c in constraints]
+    prm, fv, _, best = eng.calibrate_cf(objFn.model.base, objFn.model.time_change, lo, hi, objFn.uArray,
+                                        objFn.phiHat, objFn.r, objFn.T, nests=nestSize,
+                                        iterations=numSims, tol=tol, seed=seed, restarts=restarts)
+    return prm[best], float(fv[best])
 
 
 def generateFOEstimate(strikes, options, stock, r, t, minStrike, maxStrike):
