@@ -137,8 +137,13 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     std::copy(Th.begin(), Th.end(), x + 2 * J);
     cc.dt = 0.0;
     std::vector<int> npow;
-    if (maturity_grid(Th, &cc.dt, &npow) && !std::getenv("FOP_COS_NO_TGRID"))
-      std::memcpy(tab.data() + npow_off, npow.data(), sizeof(int) * M);
+    if (maturity_grid(Th, &cc.dt, &npow) && !std::getenv("FOP_COS_NO_TGRID")) {
+      // steps along the list: d_m = n_m - n_{m-1} (n_{-1} = 0); a descending step restarts from 1
+      std::vector<int> steps(M);
+      for (int m = 0, prev = 0; m < M; prev = npow[m], ++m)
+        steps[m] = npow[m] >= prev ? npow[m] - prev : -npow[m];
+      std::memcpy(tab.data() + npow_off, steps.data(), sizeof(int) * M);
+    }
     else
       cc.dt = 0.0;
     const double xMin = x[0], xMax = x[J - 1];

@@ -27,7 +27,7 @@ struct CosCoeffArgs {
   double r;
   const double* params;  // [P][np]
   const double* T;       // [M]
-  const int* npow;       // [M] n_m with T_m = n_m dt, or nullptr (maturities not on a common grid)
+  const int* npow;       // [M] steps d_m = n_m - n_{m-1} of T_m = n_m dt (< 0: restart), or nullptr (no common grid)
   double dt;
   const double* uk;      // [K]
   const double* vk;      // [K]
@@ -36,39 +36,51 @@ struct CosCoeffArgs {
 
 constexpr int COEFF_MAX_SPB = 64;
 
+// Running power of E = exp(-delta dt) along the maturity list (maturities on the grid T_m = n_m dt,
+// a.npow != nullptr): exp(-delta T_m) = E^{n_m} = R_{m-1} * E^{d_m}.  The host encodes d_m =
+// n_m - n_{m-1} (> 0 for an ascending list, the usual case; < 0 means "restart: E^{-d_m} from 1").
+// E^{d} comes from binary powering and is kept while consecutive steps repeat (monthly lists: 1, 2,
+// 3, 3, 3, 6, 6, 12 -> five powerings, 12 loop trips per (set, u) pair).  All branches are uniform
+// over the grid.  This replaces one exp + sincos per maturity -- a quarter of the fp64 work of a
+// Heston coefficient -- by one complex multiplication.
+struct PowState {
+  cd R, D;     // R = E^{n_{m-1}}, D = E^{dprev}
+  int dprev;
+};
+__device__ __forceinline__ cd pow_step(PowState& ps, cd E, int d) {
+  if (d < 0) {
+    ps.R = mk(1.0, 0.0);
+    d = -d;
+  }
+  if (d != ps.dprev) {
+    cd acc = mk(1.0, 0.0), S = E;
+    for (int b = d; b != 0; b >>= 1) {
+      if (b & 1) acc = acc * S;
+      S = mk(S.x * S.x - S.y * S.y, 2.0 * S.x * S.y);
+    }
+    ps.D = acc;
+    ps.dprev = d;
+  }
+  ps.R = ps.R * ps.D;
+  return ps.R;
+}
+
 // N maturities m .. m + N - 1 of one (set, u) pair, advanced operation by operation (VD<N>).
-// E = exp(-delta dt) when the maturities sit on the grid T_m = n_m dt (a.npow != nullptr): then
-// exp(-delta T_m) = E^{n_m} costs a few complex multiplications (binary powering; the bits of n_m
-// are uniform across the grid, so the branches do not diverge) instead of one exp + sincos per
-// maturity -- a quarter of the fp64 work of a Heston coefficient.
 template <int MODE, int N>
 __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, const ModelConsts& mc,
-                                            const CfPre& pre, cd E, cd u, double v, double2* crow,
-                                            int Kp, int m) {
+                                            const CfPre& pre, cd E, PowState& ps, cd u, double v,
+                                            double2* crow, int Kp, int m) {
   VD<N> Tm;
 #pragma unroll
   for (int i = 0; i < N; ++i) Tm.v[i] = __ldg(a.T + m + i);
   cx<VD<N>> lphi;
   if (MODE == CF_MODE_CIR && a.npow) {
-    int n[N], nmax = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      n[i] = __ldg(a.npow + m + i);
-      nmax = max(nmax, n[i]);
-    }
     cx<VD<N>> e;
 #pragma unroll
-    for (int i = 0; i < N; ++i) { e.x.v[i] = 1.0; e.y.v[i] = 0.0; }
-    cd S = E;
-    for (int bit = 0; (nmax >> bit) != 0; ++bit) {
-#pragma unroll
-      for (int i = 0; i < N; ++i)
-        if (n[i] >> bit & 1) {
-          const double ex = e.x.v[i], ey = e.y.v[i];
-          e.x.v[i] = ex * S.x - ey * S.y;
-          e.y.v[i] = ex * S.y + ey * S.x;
-        }
-      S = mk(S.x * S.x - S.y * S.y, 2.0 * S.x * S.y);
+    for (int i = 0; i < N; ++i) {
+      const cd r = pow_step(ps, E, __ldg(a.npow + m + i));
+      e.x.v[i] = r.x;
+      e.y.v[i] = r.y;
     }
     const cx<VD<N>> l = mk(pre.lin.x * Tm, pre.lin.y * Tm);
     lphi = cf_log_cir_given_e(mc, pre, Tm, l, e);
@@ -95,10 +107,14 @@ __device__ __forceinline__ void coeff_maturities(const CosCoeffArgs& a, const Mo
                                                  int Kp) {
   cd E = mk(1.0, 0.0);
   if (MODE == CF_MODE_CIR && a.npow) E = cexp(mk(-pre.delta.x * a.dt, -pre.delta.y * a.dt));
+  PowState ps;
+  ps.R = mk(1.0, 0.0);
+  ps.D = mk(1.0, 0.0);
+  ps.dprev = 0;
   const int M = a.M;
   int m = 0;
-  for (; m + ILP <= M; m += ILP) coeff_group<MODE, ILP>(a, mc, pre, E, u, v, crow, Kp, m);
-  for (; m < M; ++m) coeff_group<MODE, 1>(a, mc, pre, E, u, v, crow, Kp, m);
+  for (; m + ILP <= M; m += ILP) coeff_group<MODE, ILP>(a, mc, pre, E, ps, u, v, crow, Kp, m);
+  for (; m < M; ++m) coeff_group<MODE, 1>(a, mc, pre, E, ps, u, v, crow, Kp, m);
 }
 
 template <int ILP, int NT = 256, int MINB = 2>

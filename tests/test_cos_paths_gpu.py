@@ -17,6 +17,7 @@ pytestmark = pytest.mark.gpu
 ON_GRID = list(CASES.C5_T)                      # multiples of 1/12
 OFF_GRID = [0.1, 0.2718281828, 0.7, 1.3]        # no common grid
 WEEKLY = [k / 52.0 for k in (1, 2, 4, 13, 26, 52, 104)]
+DESCENDING = [2.0, 1.0, 1.0, 0.25, 0.5, 3.0]     # on a grid, not sorted, one duplicate
 
 
 @pytest.fixture(scope="module")
@@ -32,8 +33,8 @@ def _strikes(J, S0=100.0):
 
 
 @pytest.mark.parametrize("path", ["split", "fused"])
-@pytest.mark.parametrize("T", [ON_GRID, OFF_GRID, WEEKLY, [1.0], [0.5, 1.0, 1.5]],
-                         ids=["monthly", "offgrid", "weekly", "single", "three"])
+@pytest.mark.parametrize("T", [ON_GRID, OFF_GRID, WEEKLY, [1.0], [0.5, 1.0, 1.5], DESCENDING],
+                         ids=["monthly", "offgrid", "weekly", "single", "three", "unsorted"])
 @pytest.mark.parametrize("J", [66, 33, 16])
 def test_heston_paths_match_oracle(path, T, J, engine, best_oracle, monkeypatch):
     monkeypatch.setenv("FOP_COS_PATH", path)
