@@ -59,7 +59,7 @@ def workload_config(sets_per_gpu, n_gpus):
         "model": "GAUSS+CIR time change (the reference's Heston)",
         "parallelism": f"parameter sets sharded over {n_gpus} GPU(s), no data-path collective; "
                        "loss all-gather only",
-        "l2_policy": "working set per step (1 GiB coefficient matrix + 528 MB prices) >> 126 MB L2",
+        "l2_policy": "working set per step (4 GiB coefficient matrix + 528 MB prices) >> 126 MB L2",
     }
 
 
