@@ -109,3 +109,17 @@ def test_paths_agree_at_bench_size(engine, monkeypatch):
     assert np.all(np.isfinite(outs["split"]))
     err = np.abs(outs["split"] - outs["fused"])
     assert np.all(err <= 1e-9 + 1e-11 * np.abs(outs["split"])), err.max()
+
+
+@pytest.mark.parametrize("path", ["split", "fused"])
+def test_ragged_tiles_both_paths(path, engine, best_oracle, monkeypatch):
+    """Tiles that are not full: M not dividing the 64-row tile (fused: SPT * M < 64), odd strike
+    counts (scalar stores), numU not a multiple of the k-stage, one set, M > 32."""
+    monkeypatch.setenv("FOP_COS_PATH", path)
+    for P, M, J, numU in [(1, 1, 3, 64), (7, 5, 67, 100), (13, 3, 39, 256), (3, 11, 9, 17), (5, 33, 16, 40)]:
+        prm = CASES.heston_batch(P)
+        K = np.concatenate([[5000.0], np.linspace(180.0, 40.0, J - 2), [.3]])
+        T = list(np.linspace(.1, 2.0, M))
+        got = engine.cos(0, 1, prm, K, 100.0, .02, T, numU, 0)
+        ref = best_oracle.cos(0, 1, prm, K, 100.0, .02, T, numU, 0)
+        assert_parity(got, ref, what=f"{path} ragged P={P} M={M} J={J} numU={numU}")
