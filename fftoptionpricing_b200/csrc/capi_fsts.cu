@@ -11,6 +11,7 @@
 // No reordering pass exists anywhere: DIF output order == DIT input order (fft_smem.cuh).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "cf_models.cuh"
 #include "fft_engine.cuh"
@@ -21,6 +22,7 @@ using namespace fop;
 
 struct FstsArgs {
   int base, tc, np, n, P, steps, american, payoff, kind;
+  int tpb;  // paired kernel: slots per CTA
   double xmax, strike, r, Tcf, disc;  // Tcf = maturity fed to the CF (T or T/steps)
   const double* params;
   double* out;
@@ -197,6 +199,209 @@ __global__ void __launch_bounds__(256) fsts_kernel(const FstsArgs a, const doubl
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Paired variant: the value grids are REAL, so one complex transform carries two parameter sets,
+// z = v_A + i v_B.  With Z = FFT(z), the spectra separate as V_A = (Z_k + conj Z_{N-k})/2,
+// V_B = (Z_k - conj Z_{N-k})/(2i), and the step  v <- Re IFFT(V m)  for both sets at once is
+//   W_k = A_k Z_k + B_k conj(Z_{N-k}),   A = (m_A + m_B)/2,  B = (m_A - m_B)/2,   z' = IFFT(W)
+// (m Hermitian, which it is up to rounding because phi(-w) = conj phi(w); the two self-conjugate
+// bins k = 0, N/2 get Im m = 0, which is what taking the real part does to them in the
+// reference, OptionPricing.h:180,202).  Same passes, same registers (A where the unpaired kernel
+// holds m; B is read from shared memory), one extra exchange of the 16 spectrum values of a
+// thread with its partner positions pos(N - k) per step -- for twice the sets.
+__host__ __device__ inline size_t fsts_pair_slot_bytes(int n) {
+  const int N = 1 << n;
+  return 2 * (size_t)fft_padded_size(N) * sizeof(cd) + (size_t)N * 8;
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(256) fsts_pair_kernel(const FstsArgs a, const double2* __restrict__ tw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int n = LOGN, N = 1 << n, T = N >> 4;
+  const int tpb = a.tpb;  // slots per CTA (<= fft_single_tpb(n)); a slot carries two parameter sets
+  const int slot = threadIdx.x / T, b = threadIdx.x - slot * T;
+  const size_t slot_bytes = fsts_pair_slot_bytes(n);
+  cd* sm = reinterpret_cast<cd*>(smem_raw + (size_t)slot * slot_bytes);
+  cd* bsm = sm + fft_padded_size(N);
+  double* pay = reinterpret_cast<double*>(bsm + fft_padded_size(N));
+  ModelConsts* consts = reinterpret_cast<ModelConsts*>(smem_raw + (size_t)tpb * slot_bytes);
+
+  const double dx = (2.0 * a.xmax) / ((double)N - 1.0);
+  const double vmax = M_PI / dx;
+  const double du = 2.0 * vmax / N;
+  const int greek = a.kind == 0 ? 0 : a.kind == 1 ? 1 : a.kind == 2 ? 2 : 3;
+  const double scale = a.disc / (double)N;
+
+  constexpr int rl = (n & 3) == 0 ? 16 : (1 << (n & 3));
+  constexpr int np16 = ((n + 3) >> 2) - (rl == 16 ? 0 : 1);
+  constexpr int nsm = rl == 16 ? np16 - 1 : np16;
+  constexpr int S0 = N >> 4;
+  cd w[3];
+  int base[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) {
+    constexpr int SS[3] = {N >> 4 > 0 ? N >> 4 : 1, N >> 8 > 0 ? N >> 8 : 1, N >> 12 > 0 ? N >> 12 : 1};
+    const int S = SS[p];
+    w[p] = p < nsm ? tw_load<-1>(tw, (b % S) * (N / (S << 4))) : mk(1.0, 0.0);
+    base[p] = fft_base16(b, S);
+  }
+  // padded shared-memory index of the partner pos(N - k) of each of the thread's 16 positions
+  int pp[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    pp[k] = fft_pad(fft_pos((N - fft_inv_pos(16 * b + k, n)) & (N - 1), n));
+
+  for (int p0 = blockIdx.x * 2 * tpb; p0 < a.P; p0 += gridDim.x * 2 * tpb) {
+    const int cnt = min(2 * tpb, a.P - p0);
+    const int pA = p0 + 2 * slot, pB = pA + 1;
+    const bool liveA = pA < a.P, liveB = pB < a.P;
+    __syncthreads();
+    if ((int)threadIdx.x < cnt)
+      make_consts(a.base, a.tc, a.params + (size_t)(p0 + threadIdx.x) * a.np, consts[threadIdx.x]);
+    __syncthreads();
+
+    // multipliers of both sets at digit-reversed positions (an idle half repeats the last live set)
+    {
+      const int lastc = cnt - 1;
+      const ModelConsts& mcA = consts[min(2 * slot, lastc)];
+      const ModelConsts& mcB = consts[min(2 * slot + 1, lastc)];
+#pragma unroll 1
+      for (int pos = b; pos < N; pos += T) {
+        const int k = fft_inv_pos(pos, n);
+        double wk = du * k;
+        if (wk > vmax) wk -= 2.0 * vmax;  // getUDomain, OptionPricing.h:19-23 (strict >)
+        const cd u = mk(0.0, wk);
+        const bool selfconj = k == 0 || 2 * k == N;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const ModelConsts& mc = h ? mcB : mcA;
+          CfPre pre;
+          cf_prepare(a.base, a.tc, mc, u, a.r, pre);
+          const cd phi = cexp(cf_log_at(a.tc, mc, pre, a.Tcf));
+          const cd m = option_transform(greek, phi, u, a.r);
+          (h ? bsm : sm)[fft_pad(pos)] = mk(m.x * scale, selfconj ? 0.0 : m.y * scale);
+        }
+      }
+    }
+    __syncthreads();
+    cd mult[16];  // A = (m_A + m_B)/2 in registers; B = (m_A - m_B)/2 back into bsm (own positions)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int idx = fft_pad_off(16 * b, k, 1);
+      const cd m1 = sm[idx], m2 = bsm[idx];
+      mult[k] = mk(0.5 * (m1.x + m2.x), 0.5 * (m1.y + m2.y));
+      bsm[idx] = mk(0.5 * (m1.x - m2.x), 0.5 * (m1.y - m2.y));
+    }
+    __syncthreads();
+    for (int j = b; j < N; j += T) {
+      const double s = a.strike * exp(-a.xmax + dx * j);
+      pay[j] = a.payoff == 1 ? (s < a.strike ? a.strike - s : 0.0) : (s > a.strike ? s - a.strike : 0.0);
+    }
+    __syncthreads();
+    cd v[16];  // (v_A, v_B) at positions b + S0 t
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const double pj = pay[b + S0 * t];
+      v[t] = mk(pj, pj);
+    }
+
+    for (int st = 0; st < a.steps; ++st) {
+      cd x[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) x[t] = v[t];
+      if (nsm >= 1) {
+        dif16_regs_pow<-1>(x, w[0]);
+        store16_dft<-1>(sm, b, S0, x);
+        __syncthreads();
+#pragma unroll
+        for (int p = 1; p < nsm; ++p) {
+          const int S = N >> (4 * (p + 1));
+          load16(sm, base[p], S, x);
+          dif16_regs_pow<-1>(x, w[p]);
+          store16_dft<-1>(sm, base[p], S, x);
+          __syncthreads();
+        }
+        load16(sm, 16 * b, 1, x);
+      }
+      // ---- last forward pass; exchange with the partner positions; combine; first inverse pass
+      cd y[16];
+      if (rl == 16) {
+        Dft<16, -1>::run(x);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) y[k] = x[Dft<16, -1>::out(k)];
+      } else {
+        if (rl == 8) last_pass_regs<8, -1>(x);
+        else if (rl == 4) last_pass_regs<4, -1>(x);
+        else last_pass_regs<2, -1>(x);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) y[k] = x[k];
+      }
+      store16(sm, 16 * b, 1, y);  // Z at position 16 b + k (the thread's own positions: no hazard)
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const cd zp = sm[pp[k]];
+        const cd bk = bsm[fft_pad_off(16 * b, k, 1)];
+        // A Z + B conj(Zp)
+        x[k] = mk(mult[k].x * y[k].x - mult[k].y * y[k].y + bk.x * zp.x + bk.y * zp.y,
+                  mult[k].x * y[k].y + mult[k].y * y[k].x + bk.y * zp.x - bk.x * zp.y);
+      }
+      __syncthreads();  // partner reads done before the inverse passes overwrite the grid
+      if (rl == 16) {
+        Dft<16, 1>::run(x);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) y[k] = x[Dft<16, 1>::out(k)];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) x[k] = y[k];
+      } else {
+        if (rl == 8) last_pass_regs<8, 1>(x);
+        else if (rl == 4) last_pass_regs<4, 1>(x);
+        else last_pass_regs<2, 1>(x);
+      }
+      if (nsm >= 1) {
+        store16(sm, 16 * b, 1, x);
+        __syncthreads();
+#pragma unroll
+        for (int p = nsm - 1; p >= 1; --p) {
+          const int S = N >> (4 * (p + 1));
+          load16(sm, base[p], S, x);
+          dit16_regs_pow<1>(x, conj(w[p]));
+          store16_dft<1>(sm, base[p], S, x);
+          __syncthreads();
+        }
+        load16(sm, b, S0, x);
+        dit16_regs_pow<1>(x, conj(w[0]));
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = x[Dft<16, 1>::out(k)];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = x[k];
+      }
+      if (a.american) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const double pj = pay[b + S0 * k];
+          v[k] = mk(fmax(v[k].x, pj), fmax(v[k].y, pj));
+        }
+      }
+    }
+
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int j = b + S0 * k;
+      double va = v[k].x, vb = v[k].y;
+      if (a.kind == 1 || a.kind == 2) {  // delta, gamma: divide by the asset (OptionPricing.h:226,275)
+        const double s = a.strike * exp(-a.xmax + dx * j);
+        const double q = a.kind == 1 ? s : s * s;
+        va = va / q;
+        vb = vb / q;
+      }
+      if (liveA) a.out[(size_t)pA * N + j] = va;
+      if (liveB) a.out[(size_t)pB * N + j] = vb;
+    }
+  }
+}
+
 int ilog2(int N) {
   int n = 0;
   while ((1 << n) < N) ++n;
@@ -242,26 +447,35 @@ extern "C" int fop_fsts(fop_handle_t h, fop_model_t model, const double* params,
   a.Tcf = single ? T : T / steps;
   a.disc = std::exp(-r * a.Tcf);
   a.params = d_params;  a.out = d_out;
-  const int tpb = fft_single_tpb(n);
-  const size_t smem = (size_t)tpb * fsts_slot_bytes(n) + (size_t)tpb * sizeof(ModelConsts);
+  int tpb = fft_single_tpb(n);
+  // two parameter sets per complex transform whenever there are two (FOP_FSTS_PAIR=0: A/B runs)
+  const char* pe = std::getenv("FOP_FSTS_PAIR");
+  const bool pair = P >= 2 && !(pe && pe[0] == '0');
+  if (pair)  // small grids: the per-set constants, not the grids, fill shared memory
+    while (tpb > 1 && (size_t)tpb * (fsts_pair_slot_bytes(n) + 2 * sizeof(ModelConsts)) > (size_t)200 * 1024)
+      tpb >>= 1;
+  a.tpb = tpb;
+  const size_t smem = pair ? (size_t)tpb * fsts_pair_slot_bytes(n) + (size_t)2 * tpb * sizeof(ModelConsts)
+                           : (size_t)tpb * fsts_slot_bytes(n) + (size_t)tpb * sizeof(ModelConsts);
   void (*kern)(const FstsArgs, const double2*) = nullptr;
   switch (n) {
-    case 4: kern = fsts_kernel<4>; break;
-    case 5: kern = fsts_kernel<5>; break;
-    case 6: kern = fsts_kernel<6>; break;
-    case 7: kern = fsts_kernel<7>; break;
-    case 8: kern = fsts_kernel<8>; break;
-    case 9: kern = fsts_kernel<9>; break;
-    case 10: kern = fsts_kernel<10>; break;
-    case 11: kern = fsts_kernel<11>; break;
-    default: kern = fsts_kernel<12>; break;
+    case 4: kern = pair ? fsts_pair_kernel<4> : fsts_kernel<4>; break;
+    case 5: kern = pair ? fsts_pair_kernel<5> : fsts_kernel<5>; break;
+    case 6: kern = pair ? fsts_pair_kernel<6> : fsts_kernel<6>; break;
+    case 7: kern = pair ? fsts_pair_kernel<7> : fsts_kernel<7>; break;
+    case 8: kern = pair ? fsts_pair_kernel<8> : fsts_kernel<8>; break;
+    case 9: kern = pair ? fsts_pair_kernel<9> : fsts_kernel<9>; break;
+    case 10: kern = pair ? fsts_pair_kernel<10> : fsts_kernel<10>; break;
+    case 11: kern = pair ? fsts_pair_kernel<11> : fsts_kernel<11>; break;
+    default: kern = pair ? fsts_pair_kernel<12> : fsts_kernel<12>; break;
   }
   FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int groups = (P + tpb - 1) / tpb;
+  const int per_cta = pair ? 2 * tpb : tpb;
+  const int groups = (P + per_cta - 1) / per_cta;
   const int grid = std::min(groups, h->sm_count * 4);
   {
     ProfScope ps(h, "fsts_kernel");
-    kern<<<grid, fft_single_threads(n), smem, h->stream>>>(a, tw);
+    kern<<<grid, pair ? std::max(tpb * (N / 16), 1) : fft_single_threads(n), smem, h->stream>>>(a, tw);
   }
   FOP_LAUNCH_CHECK(h);
   if (out_host) {
