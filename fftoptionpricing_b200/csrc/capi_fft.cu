@@ -1,7 +1,9 @@
 // C ABI: fop_fft, fop_carr_madan  (include/fftop_b200.h)
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
+#include <vector>
 
 #include "cf_models.cuh"
 #include "fft_engine.cuh"
@@ -86,24 +88,27 @@ struct CmGen {
   int base, tc, np;
   const double* params;
   double r, T, ada, alpha, discount, b;
-  int no_skip;  // FOP_CM_NO_SKIP=1: evaluate every point (A/B runs, tests)
-  __device__ void prepare(void* aux, int p0, int count) const {
-    CmAux* ax = reinterpret_cast<CmAux*>(aux);
-    if ((int)threadIdx.x < count) {
-      CmAux& me = ax[threadIdx.x];
-      make_consts(base, tc, params + (size_t)(p0 + threadIdx.x) * np, me.mc);
-      me.c0 = 0.0;
-      me.s2t = 0.0;
-      if (tc == TC_NONE && me.mc.hs2 > 0.0 && !no_skip) {
-        const double a = alpha + 1.0;
-        const cd ja = jump_exponent(base, me.mc, mk(a, 0.0));  // real when a lies in the CF's strip
-        const double c0 = T * (a * (r - me.mc.hs2 - me.mc.comp) + me.mc.hs2 * a * a + ja.x);
-        if (ja.y == 0.0 && fabs(c0) < 1e300) {  // false for NaN
-          me.c0 = c0;
-          me.s2t = me.mc.hs2 * T;
-        }
+  int no_skip;      // FOP_CM_NO_SKIP=1: evaluate every point (A/B runs, tests)
+  const int* idx;   // optional: transform p works on parameter set idx[p]
+  __device__ void fill(CmAux& me, int p) const {
+    make_consts(base, tc, params + (size_t)(idx ? idx[p] : p) * np, me.mc);
+    me.c0 = 0.0;
+    me.s2t = 0.0;
+    if (tc == TC_NONE && me.mc.hs2 > 0.0 && !no_skip) {
+      const double a = alpha + 1.0;
+      const cd ja = jump_exponent(base, me.mc, mk(a, 0.0));  // real when a lies in the CF's strip
+      const double c0 = T * (a * (r - me.mc.hs2 - me.mc.comp) + me.mc.hs2 * a * a + ja.x);
+      if (ja.y == 0.0 && fabs(c0) < 1e300) {  // false for NaN
+        me.c0 = c0;
+        me.s2t = me.mc.hs2 * T;
       }
     }
+  }
+  // the predicate of the shortcut, shared with the cut-off kernel of the pruned path
+  __device__ static bool is_zero(const CmAux& ax, double w) { return fma(-ax.s2t, w * w, ax.c0) < -750.0; }
+  __device__ void prepare(void* aux, int p0, int count) const {
+    CmAux* ax = reinterpret_cast<CmAux*>(aux);
+    if ((int)threadIdx.x < count) fill(ax[threadIdx.x], p0 + threadIdx.x);
     __syncthreads();
   }
   // x_j = discount * phi(v + alpha + 1) / (alpha^2 + alpha + v^2 + (2 alpha + 1) v) * e^{i b j ada}
@@ -112,7 +117,7 @@ struct CmGen {
     const CmAux& ax = reinterpret_cast<const CmAux*>(aux)[p - p0];
     const ModelConsts& mc = ax.mc;
     const double w = j * ada;
-    if (fma(-ax.s2t, w * w, ax.c0) < -750.0) return mk(0.0, 0.0);
+    if (is_zero(ax, w)) return mk(0.0, 0.0);
     const cd u = mk(alpha + 1.0, w);
     CfPre pre;
     cf_prepare(base, tc, mc, u, r, pre);
@@ -131,12 +136,94 @@ struct CmEpi {
   int N;
   double S0, alpha, b, lambda, ada, discount;
   int is_put;
+  const int* idx;      // optional: transform p writes the row of parameter set idx[p]
+  // (per-index tables of the two exps, shared by the batch, were tried: the strided look-ups of
+  // the pruned path cost more L2 sectors than the exps cost fp64 issue slots -- 15.3 vs 11.3 ms)
+  __device__ double undamp(int k) const { return fm_exp(-alpha * (-b + lambda * k)); }
+  __device__ double strike_over_s0(int k) const { return fm_exp(-b + lambda * k); }
   // call_m = S0 Re(X_m) e^{-alpha(-b + lambda m)} ada/(3 pi)  (:605);  put by parity (:652)
+  __device__ double price(int k, double re) const {
+    double v = S0 * re * undamp(k) * ada / (M_PI * 3.0);
+    if (is_put) v = v - S0 + S0 * strike_over_s0(k) * discount;
+    return v;
+  }
   __device__ void operator()(int p, int k, cd X) const {
-    const double kk = -b + lambda * k;
-    double v = S0 * X.x * fm_exp(-alpha * kk) * ada / (M_PI * 3.0);
-    if (is_put) v = v - S0 + S0 * fm_exp(kk) * discount;
-    out[(size_t)p * N + k] = v;
+    out[(size_t)(idx ? idx[p] : p) * N + k] = price(k, X.x);
+  }
+};
+// ---- input-pruned Carr-Madan for long grids ----------------------------------------------------
+// When the shortcut above proves x_j = 0 for every j >= L = N / R, the N-point transform is R
+// independent L-point transforms of the pre-twiddled head, one per residue class of the output:
+//   X_{R q + s} = sum_{j < L} (x_j W_N^{j s}) W_L^{j q},   s = 0 .. R-1.
+// L <= 8192 fits the single-CTA shared-memory FFT, so the four-step transposition (16 B per point
+// written and re-read) disappears; the head x_j is generated once (cm_head_kernel) and re-read by
+// the R transforms of its set from L2.
+__global__ void cm_cutoff_kernel(CmGen g, int P, int N, int* jc_out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  CmAux ax;
+  g.fill(ax, p);
+  int jc = N;
+  if (ax.s2t > 0.0) {
+    const double w2 = fmax((ax.c0 + 750.0) / ax.s2t, 0.0);
+    const double je = sqrt(w2) / g.ada;
+    jc = je < (double)N ? (int)je : N;
+    // exact consistency with the generator's own predicate (monotone in j)
+    while (jc > 0 && CmGen::is_zero(ax, (jc - 1) * g.ada)) --jc;
+    while (jc < N && !CmGen::is_zero(ax, jc * g.ada)) ++jc;
+  }
+  jc_out[p] = jc;  // x_j = 0 for all j >= jc
+}
+// x[t][j] for the first L grid points of transform t (grid: (L / 256, transforms))
+__global__ void __launch_bounds__(256) cm_head_kernel(CmGen g, int L, cd* __restrict__ xbuf) {
+  __shared__ CmAux ax;
+  const int t = blockIdx.y;
+  if (threadIdx.x == 0) g.fill(ax, t);
+  __syncthreads();
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j < L) xbuf[(size_t)t * L + j] = g(&ax, t, t, j);
+}
+// Two residue classes per complex transform: only Re X is needed (OptionPricing.h:605), and for
+// h_j = (y_j + conj(y_{(L-j) mod L}))/2 the transform of h is exactly Re Y.  With y_j = x_j W_N^{js},
+// conj(y_{L-j}) = conj(x_{L-j}) conj(W_R^s) W_N^{js}, so
+//   z_j = h^{(s)}_j + i h^{(s+1)}_j
+//       = W_N^{js}/2 [x_j + c_s conj(x_{L-j})] + i W_N^{j(s+1)}/2 [x_j + c_{s+1} conj(x_{L-j})],
+//   c_s = e^{+2 pi i s/R};   Z_q = Re Y^{(s)}_q + i Re Y^{(s+1)}_q  ->  outputs R q + s, R q + s + 1
+// (adjacent: one 16-byte store).  Transform p of the batch = (set p >> (logR-1), pair p & (R/2-1)).
+struct PrunedGen {
+  static constexpr bool has_cf = false;  // loads and a few multiplications
+  static size_t aux_bytes(int) { return 0; }
+  const cd* xbuf;
+  const double2* twN;
+  int L, logR, N;
+  __device__ void prepare(void*, int, int) const {}
+  __device__ cd operator()(const void*, int, int p, int j) const {
+    const int t = p >> (logR - 1), s = 2 * (p & ((1 << (logR - 1)) - 1));
+    const cd* xs = xbuf + (size_t)t * L;
+    const cd x = xs[j];
+    if (j == 0) return mk(x.x, x.x);  // the self-conjugate point: Re y_0 for both residues
+    const cd xr = conj(xs[L - j]);
+    const cd w1 = tw_load<-1>(twN, (j * s) & (N - 1));
+    const cd w2 = w1 * tw_load<-1>(twN, j);
+    const cd a = w1 * (x + tw_load<1>(twN, s * L) * xr);
+    const cd b = w2 * (x + tw_load<1>(twN, (s + 1) * L) * xr);
+    return mk(0.5 * (a.x - b.y), 0.5 * (a.y + b.x));
+  }
+};
+struct PrunedEpi {
+  CmEpi inner;
+  int logR, vec2;
+  __device__ void operator()(int p, int k, cd Z) const {
+    const int t = p >> (logR - 1), s = 2 * (p & ((1 << (logR - 1)) - 1));
+    const int m = (k << logR) + s;
+    const double v0 = inner.price(m, Z.x), v1 = inner.price(m + 1, Z.y);
+    double* o = inner.out + (size_t)(inner.idx ? inner.idx[t] : t) * inner.N + m;
+    if (vec2) {
+      *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+    } else {
+      o[0] = v0;
+      o[1] = v1;
+    }
   }
 };
 
@@ -308,21 +395,94 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
   Arena ar(h);
   FOP_TRY(ar.reserve(stage_bytes(params, (size_t)P * np * 8) +
                      (out_host ? Arena::pad((size_t)chunkP * N * 8) : 0) +
-                     fft_scratch_bytes(N, (int)chunkP)));
+                     std::max(fft_scratch_bytes(N, (int)chunkP),
+                              Arena::pad((size_t)std::min<long long>(chunkP * 8192ll * 16, 512ll << 20))) +
+                     2 * Arena::pad((size_t)chunkP * 4)));
   const double* d_params = nullptr;
   FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
   double* d_tmp = out_host ? ar.alloc<double>((size_t)chunkP * N) : nullptr;
   const double b = M_PI / ada;        // getMaxK,  OptionPricing.h:31-33
   const double lambda = 2.0 * b / N;  // getLambda, :40-42
   const double discount = std::exp(-r * T);
+  const bool no_skip = std::getenv("FOP_CM_NO_SKIP") != nullptr;
+  // long grids of a Levy model: route the sets whose non-zero head fits a single-CTA transform
+  // through the input-pruned path (FOP_CM_NO_PRUNE=1: A/B runs)
+  const bool try_prune = N > 8192 && model.time_change == FOP_TC_NONE && !no_skip &&
+                         !std::getenv("FOP_CM_NO_PRUNE");
   const size_t scratch_mark = h->arena_used;
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
     const int pc = (int)std::min<long long>(chunkP, P - p0);
-    h->arena_used = scratch_mark;  // four-step scratch is re-used by every chunk
+    h->arena_used = scratch_mark;  // scratch is re-used by every chunk
     CmGen g{model.base, model.time_change, np, d_params + (size_t)p0 * np, r, T, ada, alpha, discount, b,
-            std::getenv("FOP_CM_NO_SKIP") != nullptr};
-    CmEpi e{out_host ? d_tmp : out + (size_t)p0 * N, N, S0, alpha, b, lambda, ada, discount, is_put};
-    FOP_TRY((run_fft<-1>(h, ar, N, pc, g, e)));
+            no_skip, nullptr};
+    CmEpi e{out_host ? d_tmp : out + (size_t)p0 * N, N, S0, alpha, b, lambda, ada, discount, is_put, nullptr};
+    if (!try_prune) {
+      FOP_TRY((run_fft<-1>(h, ar, N, pc, g, e)));
+    } else {
+      // 1. cut-off index of every set (device), lists per head length (host)
+      int* d_jc = ar.alloc<int>(pc);
+      int* d_idx = ar.alloc<int>(pc);
+      if (!d_jc || !d_idx) return fail(h, FOP_OOM, "arena exhausted (Carr-Madan routing)");
+      cm_cutoff_kernel<<<(pc + 127) / 128, 128, 0, h->stream>>>(g, pc, N, d_jc);
+      FOP_LAUNCH_CHECK(h);
+      std::vector<int> jc(pc);
+      FOP_CUDA(h, cudaMemcpyAsync(jc.data(), d_jc, sizeof(int) * pc, cudaMemcpyDeviceToHost, h->stream));
+      FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+      std::vector<int> lists[3];  // head <= 4096, head <= 8192, everything else (four-step)
+      for (int i = 0; i < pc; ++i) lists[jc[i] <= 4096 ? 0 : jc[i] <= 8192 ? 1 : 2].push_back(i);
+      std::vector<int> order;
+      for (auto& l : lists) order.insert(order.end(), l.begin(), l.end());
+      FOP_CUDA(h, cudaMemcpyAsync(d_idx, order.data(), sizeof(int) * pc, cudaMemcpyHostToDevice, h->stream));
+      FOP_CUDA(h, cudaStreamSynchronize(h->stream));  // `order` goes out of scope below
+      const double2* twN = nullptr;
+      FOP_TRY(get_twiddles(h, N, &twN));
+      const size_t mark2 = h->arena_used;
+      int off = 0;
+      for (int grp = 0; grp < 3; ++grp) {
+        const int cnt = (int)lists[grp].size();
+        if (cnt == 0) continue;
+        h->arena_used = mark2;
+        CmGen gg = g;
+        CmEpi ee = e;
+        if (grp == 2) {
+          gg.idx = d_idx + off;
+          ee.idx = d_idx + off;
+          FOP_TRY((run_fft<-1>(h, ar, N, cnt, gg, ee)));
+        } else {
+          const int L = grp == 0 ? 4096 : 8192, logL = grp == 0 ? 12 : 13, logR = ilog2(N) - logL;
+          // head buffers for up to `tb` sets at a time (<= 512 MiB)
+          const int tb = (int)std::min<long long>(cnt, (512ll << 20) / ((long long)L * 16));
+          cd* xbuf = ar.alloc<cd>((size_t)tb * L);
+          if (!xbuf) return fail(h, FOP_OOM, "arena exhausted (Carr-Madan head buffer)");
+          const double2* twL = nullptr;
+          FOP_TRY(get_twiddles(h, L, &twL));
+          auto kern = fft_single_kernel<-1, PrunedGen, PrunedEpi>;
+          const size_t smem = fft_single_smem(logL);
+          FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          for (int t0 = 0; t0 < cnt; t0 += tb) {
+            const int tc = std::min(tb, cnt - t0);
+            gg.idx = d_idx + off + t0;
+            ee.idx = d_idx + off + t0;
+            {
+              ProfScope ps(h, "carr_madan_head_kernel");
+              cm_head_kernel<<<dim3(L / 256, tc), 256, 0, h->stream>>>(gg, L, xbuf);
+            }
+            FOP_LAUNCH_CHECK(h);
+            PrunedGen pg{xbuf, twN, L, logR, N};
+            PrunedEpi pe{ee, logR, reinterpret_cast<uintptr_t>(ee.out) % 16 == 0 ? 1 : 0};
+            const int batch = tc << (logR - 1);  // two residue classes per transform
+            const int tpbk = fft_single_tpb(logL);
+            const int grid = std::min((batch + tpbk - 1) / tpbk, h->sm_count * 16);
+            {
+              ProfScope ps(h, "carr_madan_pruned_kernel");
+              kern<<<grid, fft_single_threads(logL), smem, h->stream>>>(logL, batch, twL, pg, pe);
+            }
+            FOP_LAUNCH_CHECK(h);
+          }
+        }
+        off += cnt;
+      }
+    }
     if (out_host)
       FOP_CUDA(h, cudaMemcpyAsync(out + (size_t)p0 * N, d_tmp, (size_t)pc * N * 8,
                                   cudaMemcpyDeviceToHost, h->stream));

@@ -57,24 +57,31 @@ __global__ void __launch_bounds__(512) fft_single_kernel(int n, int batch, const
     const bool live = slot < cnt;
     __syncthreads();
     gen.prepare(aux, p0, cnt);  // block-wide hook (per-set constants into aux shared memory)
-    // cooperative generation, natural order (consecutive threads -> consecutive j)
-    // two independent elements per trip: the (straight-line) generator code interleaves
+    // cooperative generation, natural order (consecutive threads -> consecutive j); UN independent
+    // elements per trip: two straight-line characteristic-function evaluations interleave, a
+    // load-only generator gets eight so that its L2 round trips overlap
+    constexpr int UN = Gen::has_cf ? 2 : 8;
 #pragma unroll 1
-    for (int idx = threadIdx.x; idx < cnt * N; idx += 2 * blockDim.x) {
-      const int idx1 = idx + blockDim.x;
-      const bool has1 = idx1 < cnt * N;
-      const int i1 = has1 ? idx1 : idx;
-      const int sl0 = idx >> n, j0 = idx & (N - 1), sl1 = i1 >> n, j1 = i1 & (N - 1);
-      const cd v0 = gen(aux, p0, p0 + sl0, j0);
-      const cd v1 = gen(aux, p0, p0 + sl1, j1);
-      sm0[(size_t)sl0 * psz + fft_pad(j0)] = v0;
-      if (has1) sm0[(size_t)sl1 * psz + fft_pad(j1)] = v1;
+    for (int idx = threadIdx.x; idx < cnt * N; idx += UN * blockDim.x) {
+      cd v[UN];
+#pragma unroll
+      for (int q = 0; q < UN; ++q) {
+        const int i = idx + q * blockDim.x;
+        const int ii = i < cnt * N ? i : idx;
+        v[q] = gen(aux, p0, p0 + (ii >> n), ii & (N - 1));
+      }
+#pragma unroll
+      for (int q = 0; q < UN; ++q) {
+        const int i = idx + q * blockDim.x;
+        if (i < cnt * N) sm0[(size_t)(i >> n) * psz + fft_pad(i & (N - 1))] = v[q];
+      }
     }
     __syncthreads();
     for (int ps = 0; ps < np; ++ps) {
       if (live) fft_dif_pass<SIGN>(sm, b, n, ps, tw);
       __syncthreads();
     }
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < cnt * N; idx += blockDim.x) {
       const int sl = idx >> n, k = idx & (N - 1);
       epi(p0 + sl, k, sm0[(size_t)sl * psz + fft_pad(fft_pos(k, n))]);

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from tests import cases as CASES
+from tests.conftest import assert_parity_tol, carr_madan_tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -35,6 +36,7 @@ def test_shortcut_is_bit_identical(N, model, engine, monkeypatch):
         base, tc, prm = CASES.GAUSS, 1, CASES.heston_batch(3)   # time changed: never skipped
     args = (base, tc, prm, N, 0.25, 1.5, 500.0, 0.4, 0.25)
     monkeypatch.delenv("FOP_CM_NO_SKIP", raising=False)
+    monkeypatch.setenv("FOP_CM_NO_PRUNE", "1")          # shortcut only, same transform
     fast = engine.carr_madan(*args)
     fast_put = engine.carr_madan(*args, is_put=True)
     monkeypatch.setenv("FOP_CM_NO_SKIP", "1")
@@ -42,3 +44,13 @@ def test_shortcut_is_bit_identical(N, model, engine, monkeypatch):
     full_put = engine.carr_madan(*args, is_put=True)
     assert np.array_equal(fast, full), np.max(np.abs(fast - full))
     assert np.array_equal(fast_put, full_put)
+    # default path: for N > 8192 the sets whose non-zero head fits 4096 / 8192 points go through
+    # the input-pruned transform (a different summation order: equal up to the FFT rounding
+    # noise that the undamping factor e^{-alpha k} amplifies, conftest.carr_madan_tolerance)
+    monkeypatch.delenv("FOP_CM_NO_SKIP", raising=False)
+    monkeypatch.delenv("FOP_CM_NO_PRUNE", raising=False)
+    pruned = engine.carr_madan(*args)
+    pruned_put = engine.carr_madan(*args, is_put=True)
+    tol = carr_madan_tolerance(full, N, 0.25, 1.5)
+    assert_parity_tol(pruned, full, tol, what=f"pruned vs full, {model}, N={N}")
+    assert_parity_tol(pruned_put, full_put, tol, what=f"pruned vs full (put), {model}, N={N}")
