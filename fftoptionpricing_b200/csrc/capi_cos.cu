@@ -282,6 +282,8 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ga.out = out ? (out_host ? d_out_tmp : out_k) : nullptr;
       ga.vec2 = (J % 2 == 0) && (JB % 2 == 0) && (reinterpret_cast<uintptr_t>(ga.out) % 16 == 0);
       ga.mkt = d_mkt;  ga.w = d_w;
+      ga.mvec2 = (J % 2 == 0) && (JB % 2 == 0) && (reinterpret_cast<uintptr_t>(d_mkt) % 16 == 0) &&
+                 (reinterpret_cast<uintptr_t>(d_w) % 16 == 0);
       ga.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
       const dim3 ggrid((unsigned)((rows + DM_RT - 1) / DM_RT), (unsigned)nblk);
       {

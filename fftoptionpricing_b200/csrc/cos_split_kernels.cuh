@@ -170,6 +170,7 @@ struct CosGemmArgs {
   const double* w;        // [M][J] or nullptr
   double* rowloss;        // [rows][nblk] or nullptr
   int vec2;               // prices may be stored as 16-byte pairs (J even, out 16-byte aligned)
+  int mvec2;              // mkt / w may be loaded as 16-byte pairs (J even, tables 16-byte aligned)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kern
   // of a lane are independent, so their latency overlaps (the staged, row-at-a-time version spent
   // 42 % of the warp samples waiting on its dependent load -> add -> shuffle chains,
   // profiles/r1_bench_top_kernels_ncu.json of that revision).
-  const bool vec2 = a.vec2 != 0;
+  const bool vec2 = a.vec2 != 0, mvec2 = a.mvec2 != 0;
 #pragma unroll
   for (int i = 0; i < MB; ++i) {
     const int rr = wrow + 8 * i + g;
@@ -364,13 +365,23 @@ __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kern
         }
       }
       if (mrow) {
-        if (j0 < jvalid) {
-          const double d = o0 - __ldg(mrow + j0);
-          lsum = fma((wrw ? __ldg(wrw + j0) : 1.0) * d, d, lsum);
-        }
-        if (j0 + 1 < jvalid) {
-          const double d = o1 - __ldg(mrow + j0 + 1);
-          lsum = fma((wrw ? __ldg(wrw + j0 + 1) : 1.0) * d, d, lsum);
+        if (mvec2) {  // J even, tables 16-byte aligned: one 16-byte load per table and column pair
+          if (j0 < jvalid) {
+            const double2 mk2 = __ldg(reinterpret_cast<const double2*>(mrow + j0));
+            const double2 w2 = wrw ? __ldg(reinterpret_cast<const double2*>(wrw + j0)) : make_double2(1.0, 1.0);
+            const double d0 = o0 - mk2.x, d1 = o1 - mk2.y;
+            lsum = fma(w2.x * d0, d0, lsum);
+            lsum = fma(w2.y * d1, d1, lsum);
+          }
+        } else {
+          if (j0 < jvalid) {
+            const double d = o0 - __ldg(mrow + j0);
+            lsum = fma((wrw ? __ldg(wrw + j0) : 1.0) * d, d, lsum);
+          }
+          if (j0 + 1 < jvalid) {
+            const double d = o1 - __ldg(mrow + j0 + 1);
+            lsum = fma((wrw ? __ldg(wrw + j0 + 1) : 1.0) * d, d, lsum);
+          }
         }
       }
     }
