@@ -456,7 +456,8 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
           if (!xbuf) return fail(h, FOP_OOM, "arena exhausted (Carr-Madan head buffer)");
           const double2* twL = nullptr;
           FOP_TRY(get_twiddles(h, L, &twL));
-          auto kern = fft_single_kernel<-1, PrunedGen, PrunedEpi>;
+          auto kern = grp == 0 ? fft_single_kernel<-1, PrunedGen, PrunedEpi, 12>
+                               : fft_single_kernel<-1, PrunedGen, PrunedEpi, 13>;
           const size_t smem = fft_single_smem(logL);
           FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           for (int t0 = 0; t0 < cnt; t0 += tb) {

@@ -40,10 +40,13 @@ __host__ __device__ inline size_t fft_single_smem(int n) {
   return (size_t)fft_single_tpb(n) * fft_padded_size(1 << n) * sizeof(cd);
 }
 
-template <int SIGN, typename Gen, typename Epi>
-__global__ void __launch_bounds__(512) fft_single_kernel(int n, int batch, const double2* __restrict__ tw, Gen gen,
+// LOGN > 0 fixes the transform length at compile time (index algebra of the passes and of the
+// digit reversal folds to constants); LOGN = 0 takes it from the argument.
+template <int SIGN, typename Gen, typename Epi, int LOGN = 0>
+__global__ void __launch_bounds__(512) fft_single_kernel(int n_arg, int batch, const double2* __restrict__ tw, Gen gen,
                                   Epi epi) {
   extern __shared__ __align__(16) unsigned char fft_smem_raw[];
+  const int n = LOGN > 0 ? LOGN : n_arg;
   const int N = 1 << n, T = N >> 4;
   const int tpb = fft_single_tpb(n);
   const int psz = fft_padded_size(N);
@@ -77,9 +80,17 @@ __global__ void __launch_bounds__(512) fft_single_kernel(int n, int batch, const
       }
     }
     __syncthreads();
-    for (int ps = 0; ps < np; ++ps) {
-      if (live) fft_dif_pass<SIGN>(sm, b, n, ps, tw);
-      __syncthreads();
+    if (LOGN > 0) {
+#pragma unroll
+      for (int ps = 0; ps < (LOGN + 3) / 4; ++ps) {
+        if (live) fft_dif_pass<SIGN>(sm, b, n, ps, tw);
+        __syncthreads();
+      }
+    } else {
+      for (int ps = 0; ps < np; ++ps) {
+        if (live) fft_dif_pass<SIGN>(sm, b, n, ps, tw);
+        __syncthreads();
+      }
     }
 #pragma unroll 4
     for (int idx = threadIdx.x; idx < cnt * N; idx += blockDim.x) {
