@@ -61,6 +61,10 @@ _SIGNATURES = {
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "fop_fo_estimate": (C.c_int, [_dp, _dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_int, _dp, C.c_int, _dp]),
+    "fop_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "fop_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
+    "fop_gather_losses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fop_comm_destroy": (C.c_int, [C.c_void_p]),
     "fop_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "fop_integrate_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_double, C.c_int, C.c_void_p]),

@@ -104,6 +104,7 @@ const char* fop_status_string(int status) {
     case FOP_CUDA_ERROR: return "CUDA error";
     case FOP_OOM: return "out of device memory";
     case FOP_UNSUPPORTED: return "unsupported configuration";
+    case FOP_NCCL_ERROR: return "NCCL error";
     default: return "unknown status";
   }
 }
@@ -138,6 +139,7 @@ int fop_create(fop_handle_t* handle, int device_ordinal) {
 
 int fop_destroy(fop_handle_t h) {
   if (!h) return FOP_INVALID_ARG;
+  fop_comm_destroy(h);
   cudaSetDevice(h->device);
   if (h->stream) {
     cudaStreamSynchronize(h->stream);

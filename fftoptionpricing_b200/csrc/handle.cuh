@@ -32,6 +32,9 @@ struct fop_handle_s {
     double* dev = nullptr;  // [uk | vk | x | K | T | basis]
     size_t bytes = 0;
   } cos_cache;
+  // optional NCCL communicator (capi_comm.cu; opaque here, NCCL is bound at run time)
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 0;
   // optional per-kernel device timing (fop_profile_*): accumulated by kernel name
   bool profiling = false;
   struct ProfEntry { std::string name; double ms = 0; long long launches = 0; };

@@ -202,6 +202,37 @@ class Engine:
                                          phb.ptr, ub.size, float(r), float(T), ob.ptr))
         return out
 
+    # ------------------------------------------------------------------ multi-GPU loss gather
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte NCCL id (rank 0 creates it; hand it to the other ranks by any host means)."""
+        buf = C.create_string_buffer(128)
+        st = _lib.load_library().fop_comm_unique_id(buf)
+        if st != 0:
+            raise FopError(st, "fop_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        assert len(unique_id) == 128
+        self._check(self._L.fop_comm_init(self._h, unique_id, int(rank), int(world)))
+        self._world = int(world)
+
+    def gather_losses(self, loss_local, out=None):
+        """NCCL all-gather of this rank's per-set losses: returns [world * count], rank-major.
+        numpy in -> numpy out; torch CUDA tensor in -> torch tensor out."""
+        b = _Buf(loss_local)
+        world = self._world
+        if _is_torch(loss_local):
+            import torch
+            o = out if out is not None else torch.empty(world * b.size, dtype=torch.float64,
+                                                        device=loss_local.device)
+            ob = _Buf(o)
+        else:
+            o = out if out is not None else np.empty(world * b.size)
+            ob = _Buf(o, writable=True)
+        self._check(self._L.fop_gather_losses(self._h, b.ptr, b.size, ob.ptr))
+        return o
+
     def calibrate_cf(self, base, tc, lower, upper, u, phiHat, r, T, nests=25, iterations=1500,
                      tol=1e-12, seed=42, restarts=1):
         """On-device cuckoo search over the objective of ``objfn_cf`` (replaces the reference's

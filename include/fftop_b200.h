@@ -41,7 +41,8 @@ enum fop_status {
   FOP_INVALID_ARG = 1,
   FOP_CUDA_ERROR = 2,
   FOP_OOM = 3,
-  FOP_UNSUPPORTED = 4
+  FOP_UNSUPPORTED = 4,
+  FOP_NCCL_ERROR = 5
 };
 
 /* ---- characteristic-function model descriptor ------------------------------------------------
@@ -206,6 +207,19 @@ int fop_calibrate_cf(fop_handle_t h, fop_model_t model, const double* lower, con
                      const double* u, const double* phiHat, int m, double r, double T, int nests,
                      int iterations, double tol, unsigned long long seed, int restarts,
                      double* params_out, double* fnval_out, int* iters_out, int* best_restart_out);
+
+/* ---- multi-GPU: the one collective of the path -----------------------------------
+ * One process per GPU, one handle per process.  Parameter sets are sharded contiguously over the
+ * ranks and priced without any exchange; fop_gather_losses all-gathers the per-set losses (NCCL
+ * over NVLink / NVSwitch, on the handle's stream): loss_all[world][count], rank-major.  count must
+ * be the same on every rank (pad the last shard).  Rank 0 calls fop_comm_unique_id and the host
+ * program hands the 128 bytes to the other ranks; every rank then calls fop_comm_init.  NCCL is
+ * loaded at run time (libnccl.so.2); without it these calls return FOP_NCCL_ERROR.
+ */
+int fop_comm_unique_id(char* id_out128);
+int fop_comm_init(fop_handle_t h, const char* id128, int rank, int world);
+int fop_gather_losses(fop_handle_t h, const double* loss_local, int count, double* loss_all);
+int fop_comm_destroy(fop_handle_t h);
 
 /* ---- batched FFT (the replacement for fft.hpp:49-61; exposed for parity tests) ---------------
  * In-place unnormalised transforms of `batch` contiguous length-N complex128 sequences

@@ -1,0 +1,38 @@
+"""GPU test (needs >= 2 GPUs, skipped otherwise) of the C-ABI multi-GPU path: parameter sets sharded
+over two processes / GPUs, per-set losses all-gathered with fop_gather_losses (NCCL bound at run
+time) -- every rank ends with the full loss vector in set order, identical to the single-GPU one."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.parametrize("P", [64, 37])
+def test_c_abi_loss_gather_two_gpus(P, tmp_path):
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    base = str(tmp_path / "comm")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "comm_worker.py"), str(r), "2",
+                               str(P), base], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-3000:]
+    res = [json.load(open(f"{base}.{r}.json")) for r in range(2)]
+    single = np.array(res[0]["single"])
+    for r in range(2):
+        np.testing.assert_array_equal(np.array(res[r]["full"]), single)
