@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "cos_fused_ws.cuh"
+#include "cos_gemm_variants.h"
 #include "handle.cuh"
 
 namespace fop {  // capi_cos_fused.cu
@@ -18,21 +19,24 @@ int cos_fused_launch(fop_handle_t h, CosFusedArgs& a, int NB);
 namespace {
 using namespace fop;
 
-struct GemmVariant {
-  int NB;                              // strike block JB = 8 NB columns (NB n-blocks of the MMA)
-  void (*dmma4)(const CosGemmArgs);    // 4 warps x 32 rows: fewest smem wavefronts per MMA
-  void (*dmma2)(const CosGemmArgs);    // 8 warps x 16 rows: 16 warps/SM, hides epilogues better
-};
-const GemmVariant kGemm[] = {{2, cos_gemm_dmma_kernel<2, 4>, cos_gemm_dmma_kernel<2, 2>},
-                             {4, cos_gemm_dmma_kernel<4, 4>, cos_gemm_dmma_kernel<4, 2>},
-                             {6, cos_gemm_dmma_kernel<6, 4>, cos_gemm_dmma_kernel<6, 2>},
-                             {8, cos_gemm_dmma_kernel<8, 4>, cos_gemm_dmma_kernel<8, 2>},
-                             {9, cos_gemm_dmma_kernel<9, 4>, cos_gemm_dmma_kernel<9, 2>}};
+// kernel tables live in their own translation units (capi_cos_gemm.cu, capi_cos_gemm_ex.cu) so that
+// the fourteen tensor-core instantiations compile in parallel with this file
+const GemmExVariant* pick_gemm_ex(int J) {
+  if (std::getenv("FOP_GEMM_NO_EX")) return nullptr;
+  int n = 0;
+  const GemmExVariant* t = fop::gemm_ex_variants(&n);
+  for (int i = 0; i < n; ++i)
+    if (J == 8 * t[i].NB + t[i].EX) return &t[i];
+  return nullptr;
+}
 // strike-block width that wastes the fewest padded columns (ties -> wider block)
 const GemmVariant* pick_gemm(int J, int* nblk_out) {
   const GemmVariant* best = nullptr;
   long long best_cost = 0;
-  for (const GemmVariant& v : kGemm) {
+  int nv = 0;
+  const GemmVariant* tab = fop::gemm_variants(&nv);
+  for (int iv = 0; iv < nv; ++iv) {
+    const GemmVariant& v = tab[iv];
     const int JB = 8 * v.NB, nblk = (J + JB - 1) / JB;
     const long long cost = (long long)nblk * JB;
     if (!best || cost < best_cost || (cost == best_cost && v.NB > best->NB)) {
@@ -111,9 +115,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   bool fused = false;
   if (const char* force = std::getenv("FOP_COS_PATH"))
     fused = !std::strcmp(force, "fused") && nk == 1 && fnb > 0 && spt > 0;
-  if (fused) nblk = 1;
-  const int JB = fused ? 8 * fnb : 8 * gv->NB;
-  const int Jp = fused ? dm_bs(fnb) : nblk * JB;  // row stride of the basis table
+  const GemmExVariant* gx = fused ? nullptr : pick_gemm_ex(J);
+  if (fused || gx) nblk = 1;
+  const int JB = fused ? 8 * fnb : gx ? 8 * gx->NB : 8 * gv->NB;
+  const int Jp = fused ? dm_bs(fnb) : gx ? JB + 2 : nblk * JB;  // row stride of the basis table
   // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
   const int KK = ((2 * numU + DM_KC - 1) / DM_KC) * DM_KC;
 
@@ -218,8 +223,9 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   // 66 and 1024 strikes since the epilogue runs from registers; FOP_GEMM_MB=2 selects the latter
   int mb = 4;
   if (const char* e = std::getenv("FOP_GEMM_MB")) mb = atoi(e) == 2 ? 2 : 4;
-  auto gemm_kernel = mb == 2 ? gv->dmma2 : gv->dmma4;
-  const size_t gemm_smem = cos_dmma_smem(gv->NB);
+  if (gx) mb = 4;
+  auto gemm_kernel = gx ? gx->kern : mb == 2 ? gv->dmma2 : gv->dmma4;
+  const size_t gemm_smem = cos_dmma_smem(gx ? gx->NB : gv->NB);
   FOP_CUDA(h, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
 
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
@@ -264,9 +270,8 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       {
         ProfScope ps(h, "cos_coeff_kernel");
         int ilp = M >= 2 ? 2 : 1;  // measured: 2 maturities interleaved beat 1 and 4 (register cap 128)
-        if (const char* e = std::getenv("FOP_COEFF_ILP")) ilp = std::max(1, std::min(atoi(e), M >= 4 ? 4 : M >= 2 ? 2 : 1));
-        if (ilp >= 4) cos_coeff_kernel<4><<<cgrid, 256, 0, h->stream>>>(ca);
-        else if (ilp >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
+        if (const char* e = std::getenv("FOP_COEFF_ILP")) ilp = std::max(1, std::min(atoi(e), M >= 2 ? 2 : 1));
+        if (ilp >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
         else cos_coeff_kernel<1><<<cgrid, 256, 0, h->stream>>>(ca);
       }
       FOP_LAUNCH_CHECK(h);

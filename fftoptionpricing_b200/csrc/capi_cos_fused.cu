@@ -1,5 +1,5 @@
 // Launcher of the fused warp-specialised COS kernel (cos_fused_ws.cuh); called from capi_cos.cu.
-// Kept in its own translation unit so that its six instantiations compile in parallel with the
+// Kept in its own translation unit so that its six instantiations (three strike-block widths x one or two maturities per thread) compile in parallel with the
 // split path.
 #include <algorithm>
 #include <cstdlib>
@@ -22,7 +22,7 @@ int cos_fused_consts(fop_handle_t h, int base, int tc, const double* params, int
 
 template <int NB>
 static int launch_nb(fop_handle_t h, CosFusedArgs& a, int ilp) {
-  auto kern = ilp >= 4 ? cos_fused_ws_kernel<NB, 4> : ilp >= 2 ? cos_fused_ws_kernel<NB, 2> : cos_fused_ws_kernel<NB, 1>;
+  auto kern = ilp >= 2 ? cos_fused_ws_kernel<NB, 2> : cos_fused_ws_kernel<NB, 1>;
   a.depth = fw_depth(NB, h->smem_optin);
   if (a.depth < 3) return fail(h, FOP_CUDA_ERROR, "fused COS: shared memory too small (%zu B)", h->smem_optin);
   const size_t smem = (size_t)a.depth * fw_stage_bytes(NB) + fw_tail_bytes(NB);
@@ -39,7 +39,7 @@ static int launch_nb(fop_handle_t h, CosFusedArgs& a, int ilp) {
 
 int cos_fused_launch(fop_handle_t h, CosFusedArgs& a, int NB) {
   int ilp = a.ca.M >= 2 ? 2 : 1;  // measured: 2 maturities interleaved beat 1 and 4 (register cap 128)
-  if (const char* e = std::getenv("FOP_COEFF_ILP")) ilp = std::max(1, std::min(atoi(e), a.ca.M >= 4 ? 4 : a.ca.M >= 2 ? 2 : 1));
+  if (const char* e = std::getenv("FOP_COEFF_ILP")) ilp = std::max(1, std::min(atoi(e), a.ca.M >= 2 ? 2 : 1));
   switch (NB) {
     case 2: return launch_nb<2>(h, a, ilp);
     case 5: return launch_nb<5>(h, a, ilp);

@@ -225,8 +225,13 @@ __host__ __device__ inline CosEpi cos_epi_consts(int kind, double S0, double r) 
 // MB = m-blocks (of 8 rows) per warp: MB = 4 -> 4 warps x 32 rows (72 accumulators/lane at NB = 9),
 // MB = 2 -> 8 warps x 16 rows (36 accumulators/lane, <= 128 registers -> 16 warps/SM instead of 8,
 // which keeps the DMMA pipe busier across barriers / epilogues at 1.7x the smem traffic per MMA).
-template <int NB, int MB>
+// EX = 1 or 2 remainder columns (J = 8 NB + EX, one strike block): they live in the padding of the
+// basis tile and are contracted with plain DFMAs on the A fragments the lane already holds (the
+// lane's share is kk = c mod 4; the four lanes of a row are summed after the main loop) -- 66
+// strikes cost 8 n-blocks of DMMA plus 8 DFMAs per k-step instead of 9 n-blocks.
+template <int NB, int MB, int EX = 0>
 __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kernel(const CosGemmArgs a) {
+  static_assert(EX >= 0 && EX <= 2, "at most two remainder columns fit the tile padding");
   constexpr int NT = 32 * (DM_RT / (8 * MB));
   constexpr int JB = 8 * NB, BS = dm_bs(NB);
   constexpr size_t A_BYTES = (size_t)DM_RT * DM_AS * 8;
@@ -244,12 +249,12 @@ __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kern
   const int KKp = a.KK;  // padded
   const int nchunks = KKp / DM_KC;
   const CosEpi epi = cos_epi_consts(a.kind, a.S0, a.r);
-  const int jvalid = min(JB, a.J - blk * JB);
+  const int jvalid = min(JB, a.J - blk * JB);  // columns of the DMMA tile (the EX remainder is extra)
 
   // cp.async plan (fully coalesced: consecutive threads copy consecutive 16-byte pieces).
   //   A: piece q = tid + NT i  ->  row (tid >> 4) + (NT/16) i, piece tid & 15 of the row's 256 B
   //   B: piece q = tid + NT i  ->  basis row q / BPC, piece q % BPC   (offsets precomputed)
-  constexpr int BPC = JB / 2;                          // 16-byte pieces per basis row
+  constexpr int BPC = JB / 2 + (EX ? 1 : 0);           // 16-byte pieces per basis row
   constexpr int NBI = (DM_KC * BPC + NT - 1) / NT;     // B pieces per thread
   constexpr int ARS = NT / 16;                         // A rows covered per pass
   constexpr int API = DM_RT / ARS;                     // A passes
@@ -306,6 +311,9 @@ __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kern
   for (int i = 0; i < MB; ++i)
 #pragma unroll
     for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double ex[MB][2];  // remainder columns JB, JB + 1: this lane's share of the kk sum
+#pragma unroll
+  for (int i = 0; i < MB; ++i) ex[i][0] = ex[i][1] = 0.0;
 
   const int wrow = warp * (8 * MB);
   for (int ch = 0; ch < nchunks; ++ch) {
@@ -330,6 +338,14 @@ __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kern
       for (int i = 0; i < MB; ++i)
 #pragma unroll
         for (int j = 0; j < NB; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+      if (EX > 0) {  // A[row][ks + c] * Bas[ks + c][JB + e]
+        const double2 bx = *reinterpret_cast<const double2*>(Bs - g + ks * BS + JB);
+#pragma unroll
+        for (int i = 0; i < MB; ++i) {
+          ex[i][0] = fma(af[i], bx.x, ex[i][0]);
+          if (EX > 1) ex[i][1] = fma(af[i], bx.y, ex[i][1]);
+        }
+      }
     }
     __syncthreads();
   }
@@ -382,6 +398,24 @@ __global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2) cos_gemm_dmma_kern
             const double d = o1 - __ldg(mrow + j0 + 1);
             lsum = fma((wrw ? __ldg(wrw + j0 + 1) : 1.0) * d, d, lsum);
           }
+        }
+      }
+    }
+    if (EX > 0) {  // remainder columns: sum the four kk shares, lane c = e finishes column JB + e
+      double e0 = ex[i][0], e1 = ex[i][1];
+      e0 += __shfl_xor_sync(0xffffffffu, e0, 1);
+      e0 += __shfl_xor_sync(0xffffffffu, e0, 2);
+      if (EX > 1) {
+        e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+        e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+      }
+      if (c < EX) {
+        const int jx = JB + c;
+        const double o = fma((c == 0 ? e0 : e1) - epi.sub, rs * __ldg(a.strikes + jx), epi.add);
+        if (orow) orow[jx] = o;
+        if (mrow) {
+          const double d = o - __ldg(mrow + jx);
+          lsum = fma((wrw ? __ldg(wrw + jx) : 1.0) * d, d, lsum);
         }
       }
     }
