@@ -123,3 +123,28 @@ def test_ragged_tiles_both_paths(path, engine, best_oracle, monkeypatch):
         got = engine.cos(0, 1, prm, K, 100.0, .02, T, numU, 0)
         ref = best_oracle.cos(0, 1, prm, K, 100.0, .02, T, numU, 0)
         assert_parity(got, ref, what=f"{path} ragged P={P} M={M} J={J} numU={numU}")
+
+
+@pytest.mark.parametrize("J", [33, 34, 65, 66])
+@pytest.mark.parametrize("noex", ["", "1"])
+def test_remainder_column_contraction(J, noex, engine, best_oracle, monkeypatch):
+    """J = 8 NB + 1 or 2: the remainder columns run on DFMAs next to the tensor-core tile (default)
+    or the strike block is padded (FOP_GEMM_NO_EX=1); prices, loss and every output kind."""
+    monkeypatch.setenv("FOP_COS_PATH", "split")
+    if noex:
+        monkeypatch.setenv("FOP_GEMM_NO_EX", "1")
+    else:
+        monkeypatch.delenv("FOP_GEMM_NO_EX", raising=False)
+    P = 19
+    prm = CASES.heston_batch(P)
+    K = _strikes(J)
+    T = [0.25, 0.5, 1.0]
+    for kind in (0, 1, 2, 4):
+        got = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 128, kind)
+        ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 128, kind)
+        assert_parity(got, ref, what=f"J={J} kind={kind} noex={noex!r}")
+    mkt = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm[:1], K, 100.0, 0.01, T, 128, 0)[0] * 1.02
+    w = np.ones((len(T), J))
+    got = engine.cos_loss(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 128, mkt, w)
+    ref = best_oracle.cos_loss(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 128, mkt, w)
+    assert_parity(got, ref, what=f"loss J={J} noex={noex!r}")
