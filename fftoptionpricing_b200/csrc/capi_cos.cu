@@ -89,7 +89,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   if (np == 0) return fail(h, FOP_INVALID_ARG, "unknown model (%d,%d)", model.base, model.time_change);
   if (!params || !K_desc || !T) return fail(h, FOP_INVALID_ARG, "null input pointer");
   if (!out && !loss) return fail(h, FOP_INVALID_ARG, "no output requested");
-  if (P < 0 || J < 2 || M < 1 || numU < 1 || numU > 1024 || !kinds || nk < 1 || nk > 8)
+  if (P < 0 || J < 2 || M < 1 || numU < 1 || numU > 16384 || !kinds || nk < 1 || nk > 8)
     return fail(h, FOP_INVALID_ARG, "bad sizes P=%d J=%d M=%d numU=%d nkinds=%d", P, J, M, numU, nk);
   int greek_mask = 0, plane_of[4] = {0, 0, 0, 0}, ngreeks = 0;
   for (int i = 0; i < nk; ++i) {

@@ -312,6 +312,123 @@ size_t fft_scratch_bytes(int N, int batch) {
 
 }  // namespace
 
+namespace {
+using namespace fop;
+// ---- FSTS on grids larger than the register-resident kernel of capi_fsts.cu covers (N > 4096) ----
+// Same algorithm (OptionPricing.h:155-281) through the general FFT engine: the
+// multiplier is evaluated once into HBM, every time step is forward transform (epilogue: multiply)
+// and inverse transform (epilogue: real part, early-exercise max).  Throughput path for the sizes
+// the reference's tests and BASELINE configs use is fsts_pair_kernel; this one removes the size
+// limit of the drop-in.
+struct FstsGrid {
+  int N;
+  double xmax, strike, dx;
+  int payoff;
+  __device__ double asset(int j) const { return strike * exp(-xmax + dx * j); }
+  __device__ double pay(int j) const {
+    const double sj = asset(j);
+    return payoff == 1 ? (sj < strike ? strike - sj : 0.0) : (sj > strike ? sj - strike : 0.0);
+  }
+};
+__global__ void __launch_bounds__(256) fsts_multiplier_kernel(int base, int tc, int np, const double* __restrict__ params,
+                                                              FstsGrid gr, double r, double Tcf, double scale, int greek,
+                                                              cd* __restrict__ mbuf) {
+  __shared__ ModelConsts mc;
+  const int p = blockIdx.y;
+  if (threadIdx.x == 0) make_consts(base, tc, params + (size_t)p * np, mc);
+  __syncthreads();
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= gr.N) return;
+  const double vmax = M_PI / gr.dx, du = 2.0 * vmax / gr.N;
+  double wk = du * k;
+  if (wk > vmax) wk -= 2.0 * vmax;  // getUDomain, OptionPricing.h:19-23 (strict >)
+  const cd u = mk(0.0, wk);
+  CfPre pre;
+  cf_prepare(base, tc, mc, u, r, pre);
+  const cd phi = cexp(cf_log_at(tc, mc, pre, Tcf));
+  const cd m = option_transform(greek, phi, u, r);
+  mbuf[(size_t)p * gr.N + k] = mk(m.x * scale, m.y * scale);
+}
+__global__ void fsts_payoff_kernel(FstsGrid gr, int P, double* __restrict__ v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)P * gr.N) return;
+  v[i] = gr.pay((int)(i % gr.N));
+}
+struct FstsLoadReal {
+  static constexpr bool has_cf = false;
+  static size_t aux_bytes(int) { return 0; }
+  const double* v;
+  int N;
+  __device__ void prepare(void*, int, int) const {}
+  __device__ cd operator()(const void*, int, int p, int j) const { return mk(v[(size_t)p * N + j], 0.0); }
+};
+struct FstsMulEpi {
+  const cd* m;
+  cd* y;
+  int N;
+  __device__ void operator()(int p, int k, cd X) const {
+    const size_t i = (size_t)p * N + k;
+    y[i] = X * m[i];
+  }
+};
+struct FstsRealEpi {
+  double* v;
+  FstsGrid gr;
+  int american, kind_div;  // kind_div: 0 none, 1 / asset (delta), 2 / asset^2 (gamma); last step only
+  __device__ void operator()(int p, int j, cd X) const {
+    double x = X.x;
+    if (american) x = fmax(x, gr.pay(j));
+    if (kind_div) {
+      const double sj = gr.asset(j);
+      x = kind_div == 1 ? x / sj : x / (sj * sj);
+    }
+    v[(size_t)p * gr.N + j] = x;
+  }
+};
+
+}  // namespace
+namespace fop {
+// device buffers only; d_out [P][N] receives the result
+int fsts_large_run(fop_handle_t h, Arena& ar, int base, int tc, int np, const double* d_params, int P, int N,
+                   double xmax, double strike, double r, double Tcf, double disc, int steps, int american,
+                   int payoff, int kind, double* d_out) {
+  const double dx = (2.0 * xmax) / ((double)N - 1.0);
+  FstsGrid gr{N, xmax, strike, dx, payoff};
+  const int greek = kind == 0 ? 0 : kind == 1 ? 1 : kind == 2 ? 2 : 3;
+  // sets per chunk: multiplier + spectrum (32 B per point) within 2 GiB
+  const int pcmax = (int)std::max<long long>(1, std::min<long long>(P, (2ll << 30) / ((long long)N * 32)));
+  cd* mbuf = ar.alloc<cd>((size_t)pcmax * N);
+  cd* ybuf = ar.alloc<cd>((size_t)pcmax * N);
+  if (!mbuf || !ybuf) return fail(h, FOP_OOM, "arena exhausted (large-grid FSTS)");
+  const size_t mark = h->arena_used;
+  for (int p0 = 0; p0 < P; p0 += pcmax) {
+    const int pc = std::min(pcmax, P - p0);
+    double* v = d_out + (size_t)p0 * N;
+    {
+      ProfScope ps(h, "fsts_multiplier_kernel");
+      fsts_multiplier_kernel<<<dim3((N + 255) / 256, pc), 256, 0, h->stream>>>(
+          base, tc, np, d_params + (size_t)p0 * np, gr, r, Tcf, disc / (double)N, greek, mbuf);
+    }
+    FOP_LAUNCH_CHECK(h);
+    fsts_payoff_kernel<<<(unsigned)(((size_t)pc * N + 255) / 256), 256, 0, h->stream>>>(gr, pc, v);
+    FOP_LAUNCH_CHECK(h);
+    for (int st = 0; st < steps; ++st) {
+      const bool last = st == steps - 1;
+      h->arena_used = mark;
+      FOP_TRY((run_fft<-1>(h, ar, N, pc, FstsLoadReal{v, N}, FstsMulEpi{mbuf, ybuf, N})));
+      h->arena_used = mark;
+      FOP_TRY((run_fft<1>(h, ar, N, pc, LoadGen{ybuf, N},
+                          FstsRealEpi{v, gr, american, last && (kind == 1 || kind == 2) ? kind : 0})));
+    }
+  }
+  return FOP_OK;
+}
+size_t fsts_large_bytes(int N, int P) {
+  const long long pc = std::max<long long>(1, std::min<long long>(P, (2ll << 30) / ((long long)N * 32)));
+  return 2 * Arena::pad((size_t)pc * N * 16) + fft_scratch_bytes(N, (int)pc);
+}
+}  // namespace fop
+
 extern "C" {
 
 int fop_fft(fop_handle_t h, double* data, int batch, int N, int inverse) {

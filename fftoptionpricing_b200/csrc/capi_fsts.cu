@@ -412,6 +412,11 @@ int ilog2(int N) {
 
 namespace fop {
 int get_twiddles_shared(fop_handle_t h, int N, const double2** out);  // capi_fft.cu
+// large grids (N > 4096) through the general FFT engine, capi_fft.cu
+int fsts_large_run(fop_handle_t h, Arena& ar, int base, int tc, int np, const double* d_params, int P, int N,
+                   double xmax, double strike, double r, double Tcf, double disc, int steps, int american,
+                   int payoff, int kind, double* d_out);
+size_t fsts_large_bytes(int N, int P);
 }
 
 extern "C" int fop_fsts(fop_handle_t h, fop_model_t model, const double* params, int P, int N,
@@ -421,9 +426,9 @@ extern "C" int fop_fsts(fop_handle_t h, fop_model_t model, const double* params,
   const int np = num_params(model.base, model.time_change);
   if (np == 0) return fail(h, FOP_INVALID_ARG, "unknown model (%d,%d)", model.base, model.time_change);
   if (!params || !out) return fail(h, FOP_INVALID_ARG, "null pointer");
-  if (P < 0 || N < 16 || (N & (N - 1)) || N > 4096 || steps < 1 || kind < 0 || kind > 3 ||
+  if (P < 0 || N < 16 || (N & (N - 1)) || N > (1 << 20) || steps < 1 || kind < 0 || kind > 3 ||
       payoff < 0 || payoff > 1)
-    return fail(h, FOP_INVALID_ARG, "fop_fsts: N power of two in [16, 4096], steps >= 1");
+    return fail(h, FOP_INVALID_ARG, "fop_fsts: N power of two in [16, 2^20], steps >= 1");
   if ((steps > 1 || american) && (model.time_change != FOP_TC_NONE || kind != FOP_FSTS_PRICE))
     return fail(h, FOP_UNSUPPORTED,
                 "fop_fsts: time stepping / early exercise needs a Levy model and kind = price");
@@ -432,14 +437,25 @@ extern "C" int fop_fsts(fop_handle_t h, fop_model_t model, const double* params,
   const int n = ilog2(N);
   const bool out_host = !is_device_ptr(out);
   Arena ar(h);
-  FOP_TRY(ar.reserve(stage_bytes(params, (size_t)P * np * 8) + (out_host ? Arena::pad((size_t)P * N * 8) : 0)));
+  FOP_TRY(ar.reserve(stage_bytes(params, (size_t)P * np * 8) + (out_host ? Arena::pad((size_t)P * N * 8) : 0) +
+                     (N > 4096 ? fsts_large_bytes(N, P) : 0)));
   const double* d_params = nullptr;
   FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
   double* d_out = out_host ? ar.alloc<double>((size_t)P * N) : out;
+  const bool single = steps == 1 && !american;
+  if (N > 4096) {  // beyond the register-resident kernels: general FFT engine
+    const double Tcf = single ? T : T / steps;
+    FOP_TRY(fsts_large_run(h, ar, model.base, model.time_change, np, d_params, P, N, xmax, strike, r, Tcf,
+                           std::exp(-r * Tcf), steps, american ? 1 : 0, payoff, kind, d_out));
+    if (out_host) {
+      FOP_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)P * N * 8, cudaMemcpyDeviceToHost, h->stream));
+      FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return FOP_OK;
+  }
   const double2* tw = nullptr;
   FOP_TRY(get_twiddles_shared(h, N, &tw));
 
-  const bool single = steps == 1 && !american;
   FstsArgs a;
   a.base = model.base;  a.tc = model.time_change;  a.np = np;  a.n = n;  a.P = P;
   a.steps = steps;  a.american = american ? 1 : 0;  a.payoff = payoff;  a.kind = kind;

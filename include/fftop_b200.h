@@ -131,7 +131,7 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
  * batched over P parameter sets and M maturities.
  *   K_desc [J] strikes in DESCENDING order, first and last are the synthetic far strikes
  *              (OptionPricing.h:303-312,351)
- *   T [M]      maturities;   numU <= 1024;   out [P][M][J]
+ *   T [M]      maturities;   numU <= 16384;  out [P][M][J]
  */
 int fop_cos(fop_handle_t h, fop_model_t model, const double* params, int P,
             const double* K_desc, int J, double S0, double r, const double* T, int M, int numU,
@@ -153,7 +153,8 @@ int fop_cos_greeks(fop_handle_t h, fop_model_t model, const double* params, int 
  * steps > 1 applies the one-step operator with dt = T/steps repeatedly; american != 0 takes
  * max(value, payoff) after every step (README.md:19 -- not implemented by the reference; defined
  * in SURVEY.md A.4).  steps > 1 needs a Levy model (FOP_TC_NONE) and kind FOP_FSTS_PRICE.
- * N power of two, 16 <= N <= 4096.  out [P][N]  (node j <-> asset fop_strike_underlying(-xmax,
+ * N power of two, 16 <= N <= 2^20 (N <= 4096: register-resident kernel, two sets per transform;
+ * larger grids: general FFT engine).  out [P][N]  (node j <-> asset fop_strike_underlying(-xmax,
  * xmax, strike, N)[j])
  */
 int fop_fsts(fop_handle_t h, fop_model_t model, const double* params, int P, int N, double xmax,

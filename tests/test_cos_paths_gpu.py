@@ -148,3 +148,14 @@ def test_remainder_column_contraction(J, noex, engine, best_oracle, monkeypatch)
     got = engine.cos_loss(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 128, mkt, w)
     ref = best_oracle.cos_loss(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 128, mkt, w)
     assert_parity(got, ref, what=f"loss J={J} noex={noex!r}")
+
+
+@pytest.mark.parametrize("numU", [1, 2, 1500, 4096])
+def test_many_and_few_u_terms(numU, engine, best_oracle, monkeypatch):
+    """numU far from the usual 256 (the reference takes any numUSteps, OptionPricing.h:362)."""
+    monkeypatch.setenv("FOP_COS_PATH", "split")
+    prm = CASES.heston_batch(3)
+    K = _strikes(20)
+    got = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, [0.5, 1.0], numU, 0)
+    ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, [0.5, 1.0], numU, 0)
+    assert_parity(got, ref, what=f"numU={numU}")

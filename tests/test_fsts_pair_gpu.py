@@ -71,3 +71,25 @@ def test_pairing_is_invisible(engine, monkeypatch):
     scale = 1.0 + np.abs(alone)
     assert np.max(np.abs(both - alone) / scale) < 1e-11
     assert np.max(np.abs(swapped[[1, 0, 3, 2]] - alone) / scale) < 1e-11
+
+
+@pytest.mark.parametrize("N", [8192, 16384, 65536])
+def test_large_grids_general_engine(N, engine, best_oracle):
+    """N > 4096 runs through the general FFT engine (single-CTA transform up to 8192, four-step
+    above): European single step with every output kind, and a short early-exercise loop."""
+    prm = CASES.merton_batch(3)
+    for kind in (0, 1, 2):
+        got = engine.fsts(CASES.MERTON, 0, prm, N, 5.0, 50.0, 0.03, 1.0, kind=kind)
+        ref = best_oracle.fsts(CASES.MERTON, 0, prm, N, 5.0, 50.0, 0.03, 1.0, kind=kind)
+        # gamma multiplies the spectrum by -u(1-u) ~ (pi N / (2 xmax))^2 (2.6e7 at N = 16384) and
+        # divides by asset^2 (down to 0.1): the reference's radix-2 FFT carries a twiddle-recurrence
+        # error of ~1e-12 max|X| (SURVEY section 0) that this amplifies past 1e-8 at a few nodes
+        atol = 1e-8 if (kind < 2 or N <= 8192) else 2e-7 * (N / 16384) ** 2
+        assert_parity(got, ref, atol=atol, what=f"FSTS large N={N} kind={kind}")
+    got = engine.fsts(CASES.MERTON, 0, prm, N, 7.5, 100.0, 0.05, 0.25, steps=4, american=True, payoff=1)
+    ref = best_oracle.fsts(CASES.MERTON, 0, prm, N, 7.5, 100.0, 0.05, 0.25, steps=4, american=True, payoff=1)
+    assert_parity(got, ref, what=f"American put large N={N}")
+    hes = CASES.heston_batch(2)
+    got = engine.fsts(CASES.GAUSS, 1, hes, N, 5.0, 50.0, 0.03, 1.0)
+    ref = best_oracle.fsts(CASES.GAUSS, 1, hes, N, 5.0, 50.0, 0.03, 1.0)
+    assert_parity(got, ref, what=f"FSTS large N={N} Heston")

@@ -134,7 +134,7 @@ def test_error_behaviour(engine):
     with pytest.raises(F.FopError):
         engine.cos(0, 0, [.3], [100.0], 100.0, .05, [1.0], 64, 0)       # fewer than two strikes
     with pytest.raises(F.FopError):
-        engine.cos(0, 0, [.3], [200.0, 100.0, 50.0], 100.0, .05, [1.0], 4096, 0)  # numU too large
+        engine.cos(0, 0, [.3], [200.0, 100.0, 50.0], 100.0, .05, [1.0], 100000, 0)  # numU too large
     # empty batch is a no-op
     assert engine.cos(0, 0, np.empty((0, 1)), [200.0, 100.0, 50.0], 100.0, .05, [1.0], 64, 0).shape == (0, 1, 3)
     # NaN parameters propagate (the reference validates nothing)
