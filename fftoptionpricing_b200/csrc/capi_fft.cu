@@ -512,8 +512,7 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
   Arena ar(h);
   FOP_TRY(ar.reserve(stage_bytes(params, (size_t)P * np * 8) +
                      (out_host ? Arena::pad((size_t)chunkP * N * 8) : 0) +
-                     std::max(fft_scratch_bytes(N, (int)chunkP),
-                              Arena::pad((size_t)std::min<long long>(chunkP * 8192ll * 16, 512ll << 20))) +
+                     fft_scratch_bytes(N, (int)chunkP) + (512ll << 20) + Arena::pad(512ll << 20) +
                      2 * Arena::pad((size_t)chunkP * 4)));
   const double* d_params = nullptr;
   FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
@@ -545,8 +544,15 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
       std::vector<int> jc(pc);
       FOP_CUDA(h, cudaMemcpyAsync(jc.data(), d_jc, sizeof(int) * pc, cudaMemcpyDeviceToHost, h->stream));
       FOP_CUDA(h, cudaStreamSynchronize(h->stream));
-      std::vector<int> lists[3];  // head <= 4096, head <= 8192, everything else (four-step)
-      for (int i = 0; i < pc; ++i) lists[jc[i] <= 4096 ? 0 : jc[i] <= 8192 ? 1 : 2].push_back(i);
+      // head lengths 2^12 .. 2^15 (at most N / 2); everything else takes the plain four-step path
+      constexpr int NG = 4;
+      std::vector<int> lists[NG + 1];
+      for (int i = 0; i < pc; ++i) {
+        int gsel = NG;
+        for (int q = 0; q < NG; ++q)
+          if (jc[i] <= (4096 << q) && (4096 << q) <= N / 2) { gsel = q; break; }
+        lists[gsel].push_back(i);
+      }
       std::vector<int> order;
       for (auto& l : lists) order.insert(order.end(), l.begin(), l.end());
       FOP_CUDA(h, cudaMemcpyAsync(d_idx, order.data(), sizeof(int) * pc, cudaMemcpyHostToDevice, h->stream));
@@ -555,28 +561,23 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
       FOP_TRY(get_twiddles(h, N, &twN));
       const size_t mark2 = h->arena_used;
       int off = 0;
-      for (int grp = 0; grp < 3; ++grp) {
+      for (int grp = 0; grp <= NG; ++grp) {
         const int cnt = (int)lists[grp].size();
         if (cnt == 0) continue;
         h->arena_used = mark2;
         CmGen gg = g;
         CmEpi ee = e;
-        if (grp == 2) {
+        if (grp == NG) {
           gg.idx = d_idx + off;
           ee.idx = d_idx + off;
           FOP_TRY((run_fft<-1>(h, ar, N, cnt, gg, ee)));
         } else {
-          const int L = grp == 0 ? 4096 : 8192, logL = grp == 0 ? 12 : 13, logR = ilog2(N) - logL;
+          const int logL = 12 + grp, L = 1 << logL, logR = ilog2(N) - logL;
           // head buffers for up to `tb` sets at a time (<= 512 MiB)
           const int tb = (int)std::min<long long>(cnt, (512ll << 20) / ((long long)L * 16));
           cd* xbuf = ar.alloc<cd>((size_t)tb * L);
           if (!xbuf) return fail(h, FOP_OOM, "arena exhausted (Carr-Madan head buffer)");
-          const double2* twL = nullptr;
-          FOP_TRY(get_twiddles(h, L, &twL));
-          auto kern = grp == 0 ? fft_single_kernel<-1, PrunedGen, PrunedEpi, 12>
-                               : fft_single_kernel<-1, PrunedGen, PrunedEpi, 13>;
-          const size_t smem = fft_single_smem(logL);
-          FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          const size_t mark3 = h->arena_used;
           for (int t0 = 0; t0 < cnt; t0 += tb) {
             const int tc = std::min(tb, cnt - t0);
             gg.idx = d_idx + off + t0;
@@ -589,13 +590,24 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
             PrunedGen pg{xbuf, twN, L, logR, N};
             PrunedEpi pe{ee, logR, reinterpret_cast<uintptr_t>(ee.out) % 16 == 0 ? 1 : 0};
             const int batch = tc << (logR - 1);  // two residue classes per transform
-            const int tpbk = fft_single_tpb(logL);
-            const int grid = std::min((batch + tpbk - 1) / tpbk, h->sm_count * 16);
-            {
-              ProfScope ps(h, "carr_madan_pruned_kernel");
-              kern<<<grid, fft_single_threads(logL), smem, h->stream>>>(logL, batch, twL, pg, pe);
+            if (logL <= 13) {  // single-CTA transform, length fixed at compile time
+              const double2* twL = nullptr;
+              FOP_TRY(get_twiddles(h, L, &twL));
+              auto kern = logL == 12 ? fft_single_kernel<-1, PrunedGen, PrunedEpi, 12>
+                                     : fft_single_kernel<-1, PrunedGen, PrunedEpi, 13>;
+              const size_t smem = fft_single_smem(logL);
+              FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              const int tpbk = fft_single_tpb(logL);
+              const int grid = std::min((batch + tpbk - 1) / tpbk, h->sm_count * 16);
+              {
+                ProfScope ps(h, "carr_madan_pruned_kernel");
+                kern<<<grid, fft_single_threads(logL), smem, h->stream>>>(logL, batch, twL, pg, pe);
+              }
+              FOP_LAUNCH_CHECK(h);
+            } else {  // 2^14, 2^15: the pruned transforms themselves go through the four-step engine
+              h->arena_used = mark3;
+              FOP_TRY((run_fft<-1>(h, ar, L, batch, pg, pe)));
             }
-            FOP_LAUNCH_CHECK(h);
           }
         }
         off += cnt;
