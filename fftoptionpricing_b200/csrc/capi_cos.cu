@@ -125,8 +125,11 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   // Strike-grid tables (u_k, V_k, strikes, maturities, cos/sin basis): rebuilt only when
   // (K_desc, S0, T, numU) change -- a calibration loop keeps them fixed while theta varies.
   std::vector<double> Kh(J), Th(M);
-  FOP_CUDA(h, cudaMemcpy(Kh.data(), K_desc, sizeof(double) * J, cudaMemcpyDefault));
-  FOP_CUDA(h, cudaMemcpy(Th.data(), T, sizeof(double) * M, cudaMemcpyDefault));
+  // host descriptors are read directly (a cudaMemcpy would synchronise the device on every call)
+  if (is_device_ptr(K_desc)) FOP_CUDA(h, cudaMemcpy(Kh.data(), K_desc, sizeof(double) * J, cudaMemcpyDeviceToHost));
+  else std::memcpy(Kh.data(), K_desc, sizeof(double) * J);
+  if (is_device_ptr(T)) FOP_CUDA(h, cudaMemcpy(Th.data(), T, sizeof(double) * M, cudaMemcpyDeviceToHost));
+  else std::memcpy(Th.data(), T, sizeof(double) * M);
   auto& cc = h->cos_cache;
   const size_t npow_off = 2 * (size_t)numU + 2 * (size_t)J + M;   // [M] int32 n_m, in M doubles of space
   const size_t tab_doubles = npow_off + M;
