@@ -174,14 +174,14 @@ __global__ void cm_cutoff_kernel(CmGen g, int P, int N, int* jc_out) {
   }
   jc_out[p] = jc;  // x_j = 0 for all j >= jc
 }
-// x[t][j] for the first L grid points of transform t (grid: (L / 256, transforms))
+// x[t][j] for the first L grid points of transform t: one CTA per set (the per-set constants --
+// tgamma / pow for CGMY -- are formed once), threads stride over the head
 __global__ void __launch_bounds__(256) cm_head_kernel(CmGen g, int L, cd* __restrict__ xbuf) {
   __shared__ CmAux ax;
-  const int t = blockIdx.y;
+  const int t = blockIdx.x;
   if (threadIdx.x == 0) g.fill(ax, t);
   __syncthreads();
-  const int j = blockIdx.x * 256 + threadIdx.x;
-  if (j < L) xbuf[(size_t)t * L + j] = g(&ax, t, t, j);
+  for (int j = threadIdx.x; j < L; j += 256) xbuf[(size_t)t * L + j] = g(&ax, t, t, j);
 }
 // Two residue classes per complex transform: only Re X is needed (OptionPricing.h:605), and for
 // h_j = (y_j + conj(y_{(L-j) mod L}))/2 the transform of h is exactly Re Y.  With y_j = x_j W_N^{js},
@@ -584,7 +584,7 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
             ee.idx = d_idx + off + t0;
             {
               ProfScope ps(h, "carr_madan_head_kernel");
-              cm_head_kernel<<<dim3(L / 256, tc), 256, 0, h->stream>>>(gg, L, xbuf);
+              cm_head_kernel<<<tc, 256, 0, h->stream>>>(gg, L, xbuf);
             }
             FOP_LAUNCH_CHECK(h);
             PrunedGen pg{xbuf, twN, L, logR, N};
