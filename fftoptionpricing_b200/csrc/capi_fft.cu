@@ -227,6 +227,67 @@ struct PrunedEpi {
   }
 };
 
+// Dedicated L = 4096 = 16^3 version of the pruned transform (87 % of the sets of config 4): the
+// generator feeds the first radix-16 pass in registers and the last pass feeds the epilogue from
+// registers, so the grid makes two shared-memory round trips instead of four and the digit-reversed
+// (bank-conflicting) epilogue read disappears.  One transform (= two residue classes of one set)
+// per CTA of 256 threads.
+__global__ void __launch_bounds__(256, 2) cm_pruned4096_kernel(PrunedGen pg, PrunedEpi pe, int batch,
+                                                               const double2* __restrict__ twL) {
+  constexpr int n = 12, L = 1 << n, S0 = L >> 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* sm = reinterpret_cast<cd*>(smem_raw);
+  const int b = threadIdx.x;
+  const cd w0 = tw_load<-1>(twL, b);               // W_L^{b}: pass 0 (stride 256), q = b
+  const cd w1 = tw_load<-1>(twL, (b & 15) * 16);   // W_256^{b mod 16}: pass 1 (stride 16)
+  const int base1 = fft_base16(b, 16);
+  // twiddles of the generator without per-point table traffic: j = b + 256 t, so
+  //   W_N^{j s} = W_N^{b s} W_256^{t s'},  W_N^{j} = W_N^{b} W_256^{t'}   (W_N^{256 m} = W_{N/256}^m)
+  // one strided table read per transform for W_N^{b s}; the 256 / (N/256)-periodic factors come
+  // from a table slice that stays in L1
+  const int N = pg.N, L_ = pg.L, logR = pg.logR;
+  const cd wb = tw_load<-1>(pg.twN, b);
+  // (consecutive CTAs take the R/2 transforms of one set: their 16-byte stores interleave into full
+  // sectors in L2 while they are in flight together -- one CTA doing them in turn measured 12.7 ms
+  // against 8.0 ms)
+  for (int p = blockIdx.x; p < batch; p += gridDim.x) {
+    const int tset = p >> (logR - 1), s = 2 * (p & ((1 << (logR - 1)) - 1));
+    const cd* xs = pg.xbuf + (size_t)tset * L_;
+    const cd wbs = tw_load<-1>(pg.twN, (b * s) & (N - 1));
+    const cd cs0 = tw_load<1>(pg.twN, s * L_), cs1 = tw_load<1>(pg.twN, (s + 1) * L_);
+    cd x[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int j = b + S0 * t;
+      const cd xv = xs[j];
+      if (j == 0) {
+        x[t] = mk(xv.x, xv.x);
+        continue;
+      }
+      const cd xr = conj(xs[L_ - j]);
+      const cd w1 = wbs * tw_load<-1>(pg.twN, (256 * t * s) & (N - 1));
+      const cd w2 = w1 * (wb * tw_load<-1>(pg.twN, 256 * t));
+      const cd a = w1 * (xv + cs0 * xr);
+      const cd bb = w2 * (xv + cs1 * xr);
+      x[t] = mk(0.5 * (a.x - bb.y), 0.5 * (a.y + bb.x));
+    }
+    dif16_regs_pow<-1>(x, w0);
+    store16_dft<-1>(sm, b, S0, x);
+    __syncthreads();
+    load16(sm, base1, 16, x);
+    dif16_regs_pow<-1>(x, w1);
+    store16_dft<-1>(sm, base1, 16, x);
+    __syncthreads();
+    load16(sm, 16 * b, 1, x);
+    Dft<16, -1>::run(x);
+    // position 16 b + t holds frequency k = (b >> 4) + 16 (b & 15) + 256 t  (digit reversal)
+    const int k0 = (b >> 4) + 16 * (b & 15);
+#pragma unroll
+    for (int t = 0; t < 16; ++t) pe(p, k0 + 256 * t, x[Dft<16, -1>::out(t)]);
+    __syncthreads();  // the next transform's first pass overwrites the grid
+  }
+}
+
 // ---- integrateFFT functors (fft.hpp:64-82 genericIntegration)
 struct IntGen {
   static constexpr bool has_cf = false;
@@ -590,7 +651,17 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
             PrunedGen pg{xbuf, twN, L, logR, N};
             PrunedEpi pe{ee, logR, reinterpret_cast<uintptr_t>(ee.out) % 16 == 0 ? 1 : 0};
             const int batch = tc << (logR - 1);  // two residue classes per transform
-            if (logL <= 13) {  // single-CTA transform, length fixed at compile time
+            if (logL == 12 && !std::getenv("FOP_CM_GENERIC_PRUNED")) {
+              const double2* twL = nullptr;
+              FOP_TRY(get_twiddles(h, L, &twL));
+              const size_t smem = (size_t)fft_padded_size(L) * sizeof(cd);
+              FOP_CUDA(h, cudaFuncSetAttribute(cm_pruned4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              {
+                ProfScope ps(h, "carr_madan_pruned_kernel");
+                cm_pruned4096_kernel<<<std::min(batch, h->sm_count * 16), 256, smem, h->stream>>>(pg, pe, batch, twL);
+              }
+              FOP_LAUNCH_CHECK(h);
+            } else if (logL <= 13) {  // single-CTA transform, length fixed at compile time
               const double2* twL = nullptr;
               FOP_TRY(get_twiddles(h, L, &twL));
               auto kern = logL == 12 ? fft_single_kernel<-1, PrunedGen, PrunedEpi, 12>
