@@ -570,11 +570,15 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
   const bool out_host = !is_device_ptr(out);
   // host-bound outputs are produced in chunks of <= 1 GiB of device staging
   const long long chunkP = out_host ? std::max<long long>(1, std::min<long long>(P, (1ll << 30) / ((long long)N * 8))) : P;
+  // the pruned path of long grids needs head buffers (<= 512 MiB) next to the transform scratch of
+  // its longer heads (<= 512 MiB) and two routing index arrays
+  const size_t prune_bytes = N > 8192 ? (size_t)(512ll << 20) + Arena::pad((size_t)(512ll << 20)) +
+                                            2 * Arena::pad((size_t)chunkP * 4)
+                                      : 0;
   Arena ar(h);
   FOP_TRY(ar.reserve(stage_bytes(params, (size_t)P * np * 8) +
                      (out_host ? Arena::pad((size_t)chunkP * N * 8) : 0) +
-                     fft_scratch_bytes(N, (int)chunkP) + (512ll << 20) + Arena::pad(512ll << 20) +
-                     2 * Arena::pad((size_t)chunkP * 4)));
+                     fft_scratch_bytes(N, (int)chunkP) + prune_bytes));
   const double* d_params = nullptr;
   FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
   double* d_tmp = out_host ? ar.alloc<double>((size_t)chunkP * N) : nullptr;
