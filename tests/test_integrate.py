@@ -114,3 +114,20 @@ def test_gpu_rejects_bad_arguments(engine):
         engine.integrate_fft(np.zeros(100, dtype=np.complex128), 0.0, 0.0, 1.0)   # not a power of two
     with pytest.raises(F.FopError):
         engine.integrate_fft(np.zeros(64, dtype=np.complex128), 0.0, 1.0, 1.0)    # empty range
+
+
+@pytest.mark.gpu
+def test_python_mirror_of_fft_h(best_oracle):
+    """fftoptionpricing_b200.fft: fft / ifft / integrateFFT with an ordinary callable integrand."""
+    from fftoptionpricing_b200 import fft as FM
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(256) + 1j * rng.standard_normal(256)
+    assert np.max(np.abs(FM.ifft(FM.fft(x)) / 256 - x)) < 1e-13
+    mu, sg, lo, hi, N = 0.3, 0.8, -8.0, 8.0, 1024
+    dens = lambda t: np.exp(-0.5 * ((t - mu) / sg) ** 2) / (sg * np.sqrt(2 * np.pi))
+    got = FM.integrateFFT(0.0, lo, hi, dens, N)
+    grid = lo + (hi - lo) / (N - 1) * np.arange(N)
+    ref = best_oracle.integrate_fft(dens(grid) + 0j, 0.0, lo, hi, False)
+    assert np.max(np.abs(got - ref)) <= 5e-12 * np.max(np.abs(ref))
+    doubled = FM.integrateFFT(0.0, lo, hi, dens, N, fnOutput=lambda u, v: 2.0 * v)
+    assert np.max(np.abs(doubled - 2.0 * got)) == 0.0
