@@ -8,6 +8,7 @@
 
 #include "cos_fused_ws.cuh"
 #include "cos_gemm_variants.h"
+#include "cos_host_tables.h"
 #include "handle.cuh"
 
 namespace fop {  // capi_cos_fused.cu
@@ -46,38 +47,6 @@ const GemmVariant* pick_gemm(int J, int* nblk_out) {
     }
   }
   return best;
-}
-
-// chiK / phiK of OptionPricing.h:284-300 with c = a = xMin, d = 0  (V_k = phi_k - chi_k, :342)
-double vk_put(double xMin, double u, int k) {
-  const double a = xMin, c = xMin, d = 0.0;
-  const double ed = std::exp(d), ec = std::exp(c);
-  const double chi = (std::cos(u * (d - a)) * ed - std::cos(u * (c - a)) * ec +
-                      u * std::sin(u * (d - a)) * ed - u * std::sin(u * (c - a)) * ec) /
-                     (1.0 + u * u);
-  const double phi = k == 0 ? d - c : (std::sin(u * (d - a)) - std::sin(u * (c - a))) / u;
-  return phi - chi;
-}
-
-// Common grid of the maturities: T_m = n_m dt with integers 1 <= n_m < 4096, dt = min(T) / q, to
-// within a few ulps (anything looser would change the prices).  Market maturities (weeks, months)
-// are of this form; when they are not, n stays empty and every maturity gets its own exp.
-bool maturity_grid(const std::vector<double>& T, double* dt_out, std::vector<int>* n) {
-  const double tmin = *std::min_element(T.begin(), T.end());
-  if (!(tmin > 0.0) || T.size() < 2) return false;
-  for (int q = 1; q <= 64; ++q) {
-    const double dt = tmin / q;
-    bool ok = true;
-    n->clear();
-    for (double t : T) {
-      const double ratio = t / dt, k = std::nearbyint(ratio);
-      if (k < 1.0 || k >= 4096.0 || std::fabs(ratio - k) > 2e-15 * k) { ok = false; break; }
-      n->push_back((int)k);
-    }
-    if (ok) { *dt_out = dt; return true; }
-  }
-  n->clear();
-  return false;
 }
 
 // kinds[nk]: output kinds (fop_cos_kind); out = [nk][P][M][J] (or nullptr in loss-only mode)
@@ -136,6 +105,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const bool hit = cc.dev && cc.S0 == S0 && cc.numU == numU && cc.JB == JB && cc.Jp == Jp &&
                    cc.KK == KK && cc.K == Kh && cc.T == Th;
   if (!hit) {
+    // the key is invalid until the new tables are completely in place: an early error return below
+    // must not leave the old key over new or partial tables
+    cc.numU = 0;
+    cc.K.clear();
     std::vector<double> tab(tab_doubles);
     double* uk = tab.data();
     double* vk = uk + numU;
@@ -146,10 +119,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     cc.dt = 0.0;
     std::vector<int> npow;
     if (maturity_grid(Th, &cc.dt, &npow) && !std::getenv("FOP_COS_NO_TGRID")) {
-      // steps along the list: d_m = n_m - n_{m-1} (n_{-1} = 0); a descending step restarts from 1
-      std::vector<int> steps(M);
-      for (int m = 0, prev = 0; m < M; prev = npow[m], ++m)
-        steps[m] = npow[m] >= prev ? npow[m] - prev : -npow[m];
+      const std::vector<int> steps = maturity_steps(npow);
       std::memcpy(tab.data() + npow_off, steps.data(), sizeof(int) * M);
     }
     else

@@ -42,7 +42,7 @@ struct ModelConsts {
   double speed, adaV, v0, aos2, kap1;  // CIR: aos2 = speed/adaV^2, kappa(u) = speed - kap1 u
 };
 
-__device__ __forceinline__ void make_consts(int base, int tc, const double* __restrict__ p,
+__host__ __device__ __forceinline__ void make_consts(int base, int tc, const double* __restrict__ p,
                                             ModelConsts& c) {
   c.sigma = p[0];
   c.hs2 = 0.5 * p[0] * p[0];
@@ -77,7 +77,7 @@ __device__ __forceinline__ void make_consts(int base, int tc, const double* __re
 }
 
 // uncompensated jump exponent
-__device__ __forceinline__ cd jump_exponent(int base, const ModelConsts& c, cd u) {
+__host__ __device__ __forceinline__ cd jump_exponent(int base, const ModelConsts& c, cd u) {
   if (base == BASE_MERTON) {
     // lambda (exp(u muJ + sJ^2 u^2/2) - 1)
     const cd uu = u * u;
@@ -95,7 +95,7 @@ __device__ __forceinline__ cd jump_exponent(int base, const ModelConsts& c, cd u
 
 // risk-neutral Levy exponent per unit time: u (rate - s2 - comp) + s2 u^2 + jumps(u),
 // s2 = sigma^2/2 (or 0 when the diffusion is switched off)
-__device__ __forceinline__ cd levy_exponent(int base, const ModelConsts& c, cd u, double rate,
+__host__ __device__ __forceinline__ cd levy_exponent(int base, const ModelConsts& c, cd u, double rate,
                                             double s2, bool with_jumps) {
   const double mu = rate - s2 - (with_jumps ? c.comp : 0.0);
   const cd uu = u * u;
@@ -113,7 +113,7 @@ struct CfPre {
   cd delta;  //                       (adaV == 0: kappa)
 };
 
-__device__ __forceinline__ void cf_prepare(int base, int tc, const ModelConsts& c, cd u, double r,
+__host__ __device__ __forceinline__ void cf_prepare(int base, int tc, const ModelConsts& c, cd u, double r,
                                            CfPre& pre) {
   if (tc == TC_NONE) {
     pre.lin = levy_exponent(base, c, u, r, c.hs2, true);
@@ -147,13 +147,13 @@ __device__ __forceinline__ void cf_prepare(int base, int tc, const ModelConsts& 
 //   CF_MODE_LEVY  no time change          CF_MODE_CIR  CIR clock, adaV != 0
 //   CF_MODE_DET   deterministic clock (adaV == 0, test.cpp:1187)
 enum { CF_MODE_LEVY = 0, CF_MODE_CIR = 1, CF_MODE_DET = 2 };
-__device__ __forceinline__ int cf_mode(int tc, const ModelConsts& c) {
+__host__ __device__ __forceinline__ int cf_mode(int tc, const ModelConsts& c) {
   return tc == TC_NONE ? CF_MODE_LEVY : (c.adaV == 0.0 ? CF_MODE_DET : CF_MODE_CIR);
 }
 // CIR clock, given e = exp(-delta T) (computed directly, or as a power of exp(-delta dt) when the
 // maturities sit on a common grid, see coeff_maturities) and l = lin * T
 template <class T>
-__device__ __forceinline__ cx<T> cf_log_cir_given_e(const ModelConsts& c, const CfPre& pre, T Tm,
+__host__ __device__ __forceinline__ cx<T> cf_log_cir_given_e(const ModelConsts& c, const CfPre& pre, T Tm,
                                                     cx<T> l, cx<T> e) {
   const cx<T> ome = 1.0 - e;
   const cx<T> w = 1.0 - pre.g * ome;
@@ -166,7 +166,7 @@ __device__ __forceinline__ cx<T> cf_log_cir_given_e(const ModelConsts& c, const 
 
 // T = double, or VD<N>: N maturities of the same (set, u) pair advanced operation by operation
 template <int MODE, class T>
-__device__ __forceinline__ cx<T> cf_log_at_mode(const ModelConsts& c, const CfPre& pre, T Tm) {
+__host__ __device__ __forceinline__ cx<T> cf_log_at_mode(const ModelConsts& c, const CfPre& pre, T Tm) {
   const cx<T> l = mk(pre.lin.x * Tm, pre.lin.y * Tm);
   if (MODE == CF_MODE_LEVY) return l;
   if (MODE == CF_MODE_DET) {
@@ -179,7 +179,7 @@ __device__ __forceinline__ cx<T> cf_log_at_mode(const ModelConsts& c, const CfPr
   }
   return cf_log_cir_given_e(c, pre, Tm, l, cexp(mk(-pre.delta.x * Tm, -pre.delta.y * Tm)));
 }
-__device__ __forceinline__ cd cf_log_at(int tc, const ModelConsts& c, const CfPre& pre, double T) {
+__host__ __device__ __forceinline__ cd cf_log_at(int tc, const ModelConsts& c, const CfPre& pre, double T) {
   const int mode = cf_mode(tc, c);
   if (mode == CF_MODE_LEVY) return cf_log_at_mode<CF_MODE_LEVY>(c, pre, T);
   if (mode == CF_MODE_DET) return cf_log_at_mode<CF_MODE_DET>(c, pre, T);
@@ -188,7 +188,7 @@ __device__ __forceinline__ cd cf_log_at(int tc, const ModelConsts& c, const CfPr
 
 // Option transforms applied to phi(u) (OptionPricing.h:44-73): 0 price, 1 delta, 2 gamma, 3 theta
 template <class T>
-__device__ __forceinline__ cx<T> option_transform(int greek, cx<T> phi, cd u, double r) {
+__host__ __device__ __forceinline__ cx<T> option_transform(int greek, cx<T> phi, cd u, double r) {
   if (greek == 0) return phi;
   if (greek == 1) return phi * u;
   if (greek == 2) return -(phi * (u * (1.0 - u)));

@@ -1,0 +1,129 @@
+// COS coefficients of one (parameter set, u_k) pair for every maturity (device code of
+// cos_coeff_kernel; also compiled for the host by tests/hostemu, which runs the very same source
+// against the oracle on a CPU): characteristic function -> option transform -> times V_k cp.
+#pragma once
+#include "cf_models.cuh"
+
+#ifdef __CUDA_ARCH__
+#define FOP_LDG(p) __ldg(p)
+#else
+#define FOP_LDG(p) (*(p))
+#endif
+
+namespace fop {
+
+struct CosCoeffArgs {
+  int base, tc;
+  int greek_mask;      // bit g set: emit the coefficients of transform g (0 price 1 delta 2 gamma 3 theta)
+  size_t plane;        // doubles between the coefficient matrices of consecutive emitted transforms
+  int P, M, K, Kp, np, spb;  // Kp = padded u count (row stride of C = 2 Kp); spb = sets per block
+  double r;
+  const double* params;  // [P][np]
+  const double* T;       // [M]
+  const int* npow;       // [M] steps d_m = n_m - n_{m-1} of T_m = n_m dt (< 0: restart), or nullptr (no common grid)
+  double dt;
+  const double* uk;      // [K]
+  const double* vk;      // [K]
+  double* C;             // [n_greeks][P*M][2 Kp]
+};
+
+constexpr int COEFF_MAX_SPB = 64;
+
+// Running power of E = exp(-delta dt) along the maturity list (maturities on the grid T_m = n_m dt,
+// a.npow != nullptr): exp(-delta T_m) = E^{n_m} = R_{m-1} * E^{d_m}.  The host encodes d_m =
+// n_m - n_{m-1} (> 0 for an ascending list, the usual case; < 0 means "restart: E^{-d_m} from 1").
+// E^{d} comes from binary powering and is kept while consecutive steps repeat (monthly lists: 1, 2,
+// 3, 3, 3, 6, 6, 12 -> five powerings, 12 loop trips per (set, u) pair).  All branches are uniform
+// over the grid.  This replaces one exp + sincos per maturity -- a quarter of the fp64 work of a
+// Heston coefficient -- by one complex multiplication.
+struct PowState {
+  cd R, D;     // R = E^{n_{m-1}}, D = E^{dprev}
+  int dprev;
+};
+__host__ __device__ __forceinline__ cd pow_step(PowState& ps, cd E, int d) {
+  if (d < 0) {
+    ps.R = mk(1.0, 0.0);
+    d = -d;
+  }
+  if (d != ps.dprev) {
+    cd acc = mk(1.0, 0.0), S = E;
+    for (int b = d; b != 0; b >>= 1) {
+      if (b & 1) acc = acc * S;
+      S = mk(S.x * S.x - S.y * S.y, 2.0 * S.x * S.y);
+    }
+    ps.D = acc;
+    ps.dprev = d;
+  }
+  ps.R = ps.R * ps.D;
+  return ps.R;
+}
+
+// N maturities m .. m + N - 1 of one (set, u) pair, advanced operation by operation (VD<N>).
+template <int MODE, int N>
+__host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, const ModelConsts& mc,
+                                            const CfPre& pre, cd E, PowState& ps, cd u, double v,
+                                            double2* crow, int Kp, int m) {
+  VD<N> Tm;
+#pragma unroll
+  for (int i = 0; i < N; ++i) Tm.v[i] = FOP_LDG(a.T + m + i);
+  cx<VD<N>> lphi;
+  if (MODE == CF_MODE_CIR && a.npow) {
+    cx<VD<N>> e;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const cd r = pow_step(ps, E, FOP_LDG(a.npow + m + i));
+      e.x.v[i] = r.x;
+      e.y.v[i] = r.y;
+    }
+    const cx<VD<N>> l = mk(pre.lin.x * Tm, pre.lin.y * Tm);
+    lphi = cf_log_cir_given_e(mc, pre, Tm, l, e);
+  } else {
+    lphi = cf_log_at_mode<MODE>(mc, pre, Tm);
+  }
+  const cx<VD<N>> d = cexp(lphi);
+  // one CF evaluation feeds every requested transform (price / delta / gamma / theta)
+  double2* cg = crow;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (!(a.greek_mask >> g & 1)) continue;
+    const cx<VD<N>> t = option_transform(g, d, u, a.r);
+#pragma unroll
+    for (int i = 0; i < N; ++i) cg[(size_t)(m + i) * Kp] = make_double2(t.x.v[i] * v, t.y.v[i] * v);
+    cg += a.plane / 2;
+  }
+}
+
+// all maturities of one (set, u) pair, ILP at a time
+template <int MODE, int ILP>
+__host__ __device__ __forceinline__ void coeff_maturities(const CosCoeffArgs& a, const ModelConsts& mc,
+                                                 const CfPre& pre, cd u, double v, double2* crow,
+                                                 int Kp) {
+  cd E = mk(1.0, 0.0);
+  if (MODE == CF_MODE_CIR && a.npow) E = cexp(mk(-pre.delta.x * a.dt, -pre.delta.y * a.dt));
+  PowState ps;
+  ps.R = mk(1.0, 0.0);
+  ps.D = mk(1.0, 0.0);
+  ps.dprev = 0;
+  const int M = a.M;
+  int m = 0;
+  for (; m + ILP <= M; m += ILP) coeff_group<MODE, ILP>(a, mc, pre, E, ps, u, v, crow, Kp, m);
+  for (; m < M; ++m) coeff_group<MODE, 1>(a, mc, pre, E, ps, u, v, crow, Kp, m);
+}
+
+// Output map of the reference entry points (OptionPricing.h:378,414,439,464,490,515,541) as
+//   out = (val - sub) * (disc * K * inv) + add      with per-kind uniform scalars
+struct CosEpi { double sub, inv, add; };
+__host__ __device__ inline CosEpi cos_epi_consts(int kind, double S0, double r) {
+  switch (kind) {
+    case 0: return {1.0, 1.0, S0};               // call price  (val-1) disc K + S0
+    case 1: return {0.0, 1.0, 0.0};              // put price    val disc K
+    case 2: return {0.0, 1.0 / S0, 1.0};         // call delta   val disc K / S0 + 1
+    case 3: return {0.0, 1.0 / S0, 0.0};         // put delta
+    case 4:
+    case 5: return {0.0, 1.0 / (S0 * S0), 0.0};  // gamma
+    case 6: return {r, 1.0, 0.0};                // call theta  (val - r) disc K
+    default: return {0.0, 1.0, 0.0};             // put theta
+  }
+}
+
+}  // namespace fop

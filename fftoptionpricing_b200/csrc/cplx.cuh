@@ -77,7 +77,7 @@ template <class T> CX_HD void cdiv_clog_unit(cx<T> a, cx<T> w, cx<T>* q, cx<T>* 
   *lw = mk(0.5 * fm_log_pos(n), fm_atan2_normal(w.y, w.x));
 }
 // principal square root (Re >= 0; on the negative real axis the sign of Im follows the sign of z.y)
-__device__ __forceinline__ cd csqrt(cd z) {
+__host__ __device__ __forceinline__ cd csqrt(cd z) {
   if (z.x == 0.0 && z.y == 0.0) return mk(0.0, z.y);
   const double r = sqrt(z.x * z.x + z.y * z.y);
   if (z.x >= 0.0) {

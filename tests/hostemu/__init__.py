@@ -1,0 +1,60 @@
+"""TEST INFRASTRUCTURE ONLY: builds and loads the CPU emulation of the device CF code (emu.cu)."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SO = os.path.join(HERE, "libfop_hostemu.so")
+_dp = C.POINTER(C.c_double)
+
+
+def build(force=False):
+    src = os.path.join(HERE, "emu.cu")
+    inc = os.path.join(ROOT, "fftoptionpricing_b200", "csrc")
+    deps = [src] + [os.path.join(inc, f) for f in ("fmath.cuh", "cplx.cuh", "cf_models.cuh", "cos_coeff.cuh",
+                                                   "cos_host_tables.h")]
+    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
+        return SO
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        return None
+    r = subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler",
+                        "-fPIC,-fopenmp,-mfma", "-shared", "-I", inc, "-o", SO, src],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("hostemu build failed:\n" + r.stderr[-3000:])
+    return SO
+
+
+class HostEmu:
+    def __init__(self):
+        so = build()
+        if so is None:
+            raise FileNotFoundError("nvcc not available")
+        self.lib = C.CDLL(so)
+        i, d = C.c_int, C.c_double
+        self.lib.emu_cos.argtypes = [i, i, _dp, i, _dp, i, d, d, _dp, i, i, i, i, _dp]
+        self.lib.emu_logcf.argtypes = [i, i, _dp, d, d, d, d, _dp]
+
+    def cos(self, base, tc, params, K, S0, r, T, numU, kind=0, use_tgrid=True):
+        K = np.ascontiguousarray(K, dtype=np.float64)
+        T = np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        P = p.size // {0: 1, 1: 4, 2: 5}[base] if tc == 0 else p.size // ({0: 1, 1: 4, 2: 5}[base] + 4)
+        out = np.empty((P, T.size, K.size))
+        rc = self.lib.emu_cos(base, tc, p.ctypes.data_as(_dp), P, K.ctypes.data_as(_dp), K.size, S0, r,
+                              T.ctypes.data_as(_dp), T.size, numU, kind, int(use_tgrid),
+                              out.ctypes.data_as(_dp))
+        assert rc == 0
+        return out
+
+    def logcf(self, base, tc, params, r, T, u: complex):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        o = np.empty(2)
+        assert self.lib.emu_logcf(base, tc, p.ctypes.data_as(_dp), r, T, u.real, u.imag,
+                                  o.ctypes.data_as(_dp)) == 0
+        return complex(o[0], o[1])

@@ -36,3 +36,23 @@ def test_c_abi_loss_gather_two_gpus(P, tmp_path):
     single = np.array(res[0]["single"])
     for r in range(2):
         np.testing.assert_array_equal(np.array(res[r]["full"]), single)
+
+
+def test_c_abi_loss_gather_world_1_host_and_device_pointers():
+    """Single-GPU coverage of the library's own collective: dlopen of libnccl,
+    ncclCommInitRank with world = 1, fop_gather_losses through the host-staging path and the
+    device-pointer path; the gathered vector is the input."""
+    import torch
+
+    import fftoptionpricing_b200 as F
+    eng = F.Engine(0)
+    try:
+        eng.comm_init(F.Engine.comm_unique_id(), 0, 1)
+        x = np.random.default_rng(3).random(1000)
+        np.testing.assert_array_equal(eng.gather_losses(x), x)
+        xd = torch.tensor(x, device="cuda:0")
+        yd = eng.gather_losses(xd)
+        eng.synchronize()
+        assert torch.equal(yd, xd)
+    finally:
+        eng.close()

@@ -1,0 +1,271 @@
+"""Bench-scale parity sweeps: the CUDA path against the oracle (the reference's own headers,
+oracle/_ref, when present) on the SAME inputs at the sizes the benchmark actually prices, not on a
+handful of sampled sets.  Every test prints the worst parameter set (index, parameters, error /
+tolerance) so that an outlier can be investigated; the tolerance is the north-star one
+(1e-8 + 1e-10 |ref|) and is never widened here -- the single documented exception is the
+Carr-Madan noise floor outside the reference's own test window (conftest.carr_madan_tolerance),
+whose extent is reported per configuration by the test itself.
+
+Reference entry points: FangOostCallPrice OptionPricing.h:362-382, CarrMadanCall :670-681,
+FSTSGeneric :155-184 (+ SURVEY A.4 for the time loop); parameter boxes generateCharts.cpp:217-223,
+283-289, 324-329.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from tests import cases as CASES
+from tests.conftest import ATOL, RTOL, carr_madan_tolerance
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import fftoptionpricing_b200 as F
+    eng = F.Engine(0)
+    yield eng
+    eng.close()
+
+
+def sweep_report(got, ref, params, what, tol=None):
+    """Per-set max(err / tol); prints the worst sets; returns (ratio per set, n outside)."""
+    P = params.shape[0]
+    got = np.asarray(got, dtype=np.float64).reshape(P, -1)
+    ref = np.asarray(ref, dtype=np.float64).reshape(P, -1)
+    tol = (ATOL + RTOL * np.abs(ref)) if tol is None else np.asarray(tol).reshape(P, -1)
+    err = np.abs(got - ref)
+    both_nan = np.isnan(got) & np.isnan(ref)
+    ratio = np.where(both_nan, 0.0, err / tol)
+    ratio = np.where(np.isnan(ratio), np.inf, ratio)      # NaN on one side only is a failure
+    per_set = ratio.max(axis=1)
+    order = np.argsort(-per_set)[:3]
+    print(f"\n[{what}] sets={P} outputs={got.size} max err/tol={per_set.max():.3e} "
+          f"median={np.median(per_set):.3e} sets over tol={int((per_set > 1).sum())}")
+    for i in order:
+        j = int(np.argmax(ratio[i]))
+        print(f"    set {int(i)} params={np.array2string(params[i], precision=6)} out[{j}] got={got[i, j]!r} "
+              f"ref={ref[i, j]!r} err/tol={per_set[i]:.3e}")
+    return per_set, int((ratio > 1).sum())
+
+
+# ------------------------------------------------------------------------------------------------
+def test_c5_sweep_100000_heston_sets_x8x66_prices_and_loss_vs_oracle(engine, best_oracle):
+    """(a) 100 000 Heston sets x 8 maturities x 66 strikes of the bench workload (same seed, same
+    market, same weights as bench.py): every price and every per-set loss against the oracle."""
+    P = 100_000
+    K, T, w = CASES.c5_strikes(), CASES.C5_T, CASES.c5_weights()
+    prm = CASES.heston_batch(P)
+    mkt = np.array([[CASES.bs_call(100.0, 1.0, k, 0.25, t) for k in K] for t in T])
+    loss, prices = engine.cos_loss(0, 1, prm, K, 100.0, 0.0, T, 256, mkt, w, want_prices=True)
+    rloss, rprices = best_oracle.cos_loss(0, 1, prm, K, 100.0, 0.0, T, 256, mkt, w, want_prices=True)
+    per_set, nbad = sweep_report(prices, rprices, prm, "C5 prices 100000x8x66")
+    assert nbad == 0, f"{nbad} prices outside 1e-8 + 1e-10|ref|"
+    per_set_l, nbad_l = sweep_report(loss, rloss, prm, "C5 per-set loss 100000")
+    assert nbad_l == 0, f"{nbad_l} losses outside 1e-8 + 1e-10|ref|"
+    # loss-only call (prices_out == NULL) must give the very same losses
+    loss2 = engine.cos_loss(0, 1, prm, K, 100.0, 0.0, T, 256, mkt, w)
+    assert np.array_equal(loss, loss2)
+
+
+def test_c2_sweep_2048_heston_sets_x1024_strikes_vs_oracle(engine, best_oracle):
+    """Config 2 (256 u x 1024 strikes, one maturity): 2048 sets, every price."""
+    P = 2048
+    prm = CASES.heston_batch(P, seed=CASES.SEED + 7)
+    K = CASES.fang_oost_strikes(-5.0, 5.0, 100.0, 1024)
+    got = engine.cos(0, 1, prm, K, 100.0, 0.0, [1.0], 256, 0)
+    ref = best_oracle.cos(0, 1, prm, K, 100.0, 0.0, [1.0], 256, 0)
+    _, nbad = sweep_report(got, ref, prm, "C2 prices 2048x1024")
+    assert nbad == 0
+
+
+def test_c3_american_4096_merton_sets_128_sampled_vs_oracle(engine, best_oracle):
+    """(b) config 3 at its full batch (4096 Merton sets, N = 4096, 256 steps, American put): 128
+    evenly sampled sets against the oracle's time loop, all 4096 nodes each."""
+    P = 4096
+    prm = CASES.merton_batch(P)
+    am = engine.fsts(1, 0, prm, 4096, 7.5, 100.0, .05, .25, steps=256, american=True, payoff=1)
+    idx = np.linspace(0, P - 1, 128).astype(int)
+    ref = best_oracle.fsts(1, 0, prm[idx], 4096, 7.5, 100.0, .05, .25, steps=256, american=True, payoff=1)
+    _, nbad = sweep_report(am[idx], ref, prm[idx], "C3 American put 128 of 4096 sets x 4096 nodes")
+    assert nbad == 0
+    S = CASES.strike_underlying(-7.5, 7.5, 100.0, 4096)
+    assert np.all(am >= np.maximum(100.0 - S, 0.0)[None] - 1e-12)
+
+
+@pytest.mark.parametrize("route", ["default", "four_step"])
+def test_c4_carr_madan_65536_256_cgmy_sets_vs_oracle(route, engine, best_oracle, monkeypatch):
+    """(c) config 4 grid (N = 2^16) on 256 CGMY sets, through the input-pruned route (default) and
+    the plain four-step route (FOP_CM_NO_PRUNE=1).  Inside the reference's own test window
+    [0.3N, 0.7N) the tolerance is the north-star one; outside, the reference's FFT noise floor is
+    added (conftest.carr_madan_tolerance) and the test reports how many outputs needed it."""
+    P, N = 256, 65536
+    monkeypatch.delenv("FOP_CM_NO_SKIP", raising=False)
+    if route == "four_step":
+        monkeypatch.setenv("FOP_CM_NO_PRUNE", "1")
+    else:
+        monkeypatch.delenv("FOP_CM_NO_PRUNE", raising=False)
+    prm = CASES.cgmy_batch(P)
+    got = engine.carr_madan(2, 0, prm, N, .25, 1.5, 500.0, .4, .25, False)
+    ref = best_oracle.carr_madan(2, 0, prm, N, .25, 1.5, 500.0, .4, .25, False)
+    lo, hi = int(N * .3), int(N * .7)
+    _, nbad_win = sweep_report(got[:, lo:hi], ref[:, lo:hi], prm, f"C4 {route}: window [0.3N,0.7N) 256x{hi - lo}")
+    assert nbad_win == 0
+    tol = carr_madan_tolerance(ref, N, .25, 1.5).reshape(P, N)
+    _, nbad = sweep_report(got, ref, prm, f"C4 {route}: all 256x65536 with the noise floor outside the window", tol=tol)
+    strict = ATOL + RTOL * np.abs(ref)
+    err = np.abs(got - ref)
+    outside = np.ones(N, dtype=bool)
+    outside[lo:hi] = False
+    need = (err > strict) & outside[None]
+    print(f"    outputs outside the window that need the noise floor: {int(need.sum())} of {P * int(outside.sum())} "
+          f"(max err/strict tol {float((err / strict)[:, outside].max()):.3e})")
+    assert nbad == 0
+
+
+# ------------------------------------------------------------------------------------------------
+def _heston_edges():
+    rows = []
+    base = CASES.heston0()
+    for rho in (-1.0, -0.999, 0.999, 1.0):
+        for adaV in (1e-4, 0.3, 4.0):
+            for v0 in (1e-6, 1.0):
+                for speed in (0.1, 2.0):
+                    rows.append([base[0], speed, adaV, rho, v0])
+    for sig in (0.05, 0.6):
+        rows.append([sig, 1.0, 1e-4, -0.5, 1e-6])
+        rows.append([sig, 1.0, 4.0, 1.0, 2.0])
+    return np.array(rows)
+
+
+def assert_parity_or_reference_noise(got, ref, prm, exact_fn, what, factor=5.0):
+    """North-star parity for every parameter set; a set that misses it is accepted ONLY when the
+    reference's own double-precision result misses the exact value of the reference's formula
+    (40-digit evaluation, tests/mp_exact.py) by more than the tolerance as well -- i.e. the reference
+    output is rounding noise there -- and the CUDA result is no further from the exact value than
+    `factor` x the reference is.  Both distances are printed."""
+    per_set, nbad = sweep_report(got, ref, prm, what)
+    noisy = np.nonzero(per_set > 1.0)[0]
+    P = prm.shape[0]
+    got, ref = np.asarray(got).reshape(P, -1), np.asarray(ref).reshape(P, -1)
+    for i in noisy:
+        ex = np.asarray(exact_fn(prm[i])).reshape(-1)
+        tol = ATOL + RTOL * np.abs(ex)
+        r_ref = float((np.abs(ref[i] - ex) / tol).max())
+        r_gpu = float((np.abs(got[i] - ex) / tol).max())
+        print(f"    set {int(i)} {np.array2string(prm[i], precision=6)}: |ref-exact|/tol={r_ref:.3e} "
+              f"|gpu-exact|/tol={r_gpu:.3e} |gpu-ref|/tol={per_set[i]:.3e}")
+        assert r_ref > 1.0, f"{what}: set {i} misses parity although the reference is exact to tolerance"
+        assert r_gpu <= factor * r_ref, f"{what}: set {i} is further from the exact value than the reference"
+    return len(noisy)
+
+
+def test_heston_box_edges_cos_vs_oracle(engine, best_oracle):
+    """(d) edges of the Heston box: |rho| in {0.999, 1}, adaV 1e-4 (next to the exact adaV == 0
+    branch), v0Hat 1e-6, slow / fast mean reversion; bench strike grid and maturities.  The sets
+    with adaV = 1e-4 are ill-conditioned IN THE REFERENCE (cirLogMGF forms (delta - kappa) speed /
+    adaV^2 with delta = sqrt(kappa^2 + 2 psi adaV^2): eight digits cancel); see
+    assert_parity_or_reference_noise."""
+    from tests import mp_exact as MP
+    prm = _heston_edges()
+    K, T = CASES.c5_strikes(), CASES.C5_T
+    got = engine.cos(0, 1, prm, K, 100.0, 0.0, T, 256, 0)
+    ref = best_oracle.cos(0, 1, prm, K, 100.0, 0.0, T, 256, 0)
+    n = assert_parity_or_reference_noise(
+        got, ref, prm, lambda p: MP.cos_call_prices(0, 1, p, K, 100.0, 0.0, T, 256),
+        f"Heston box edges {len(prm)}x8x66")
+    well = prm[:, 2] > 1e-3
+    per_set, _ = sweep_report(got[well], ref[well], prm[well], "Heston box edges, adaV > 1e-3")
+    assert per_set.max() <= 1.0 and n <= int((~well).sum())
+
+
+def test_heston_tiny_adaV_is_reference_noise(engine, best_oracle):
+    """adaV = 1e-5 ... 1e-8: the reference's own prices are wrong in the 4th ... 1st digit there (its
+    cancellation error is amplified by speed / adaV^2 up to 1e16); the CUDA path follows the same
+    formula and must stay as close to the exact value as the reference does."""
+    from tests import mp_exact as MP
+    prm = np.array([[0.2, 1.0, 1e-8, -0.5, 1.0], [0.3, 0.5, 1e-8, 0.9, 0.5], [0.3, 0.5, 1e-6, 0.9, 0.5],
+                    [0.3, 0.5, 1e-5, 0.9, 0.5]])
+    K, T = CASES.c5_strikes(), CASES.C5_T
+    got = engine.cos(0, 1, prm, K, 100.0, 0.0, T, 256, 0)
+    ref = best_oracle.cos(0, 1, prm, K, 100.0, 0.0, T, 256, 0)
+    assert_parity_or_reference_noise(
+        got, ref, prm, lambda p: MP.cos_call_prices(0, 1, p, K, 100.0, 0.0, T, 256),
+        "Heston adaV 1e-8..1e-5")
+
+
+def test_cgmy_box_edges_vs_oracle(engine, best_oracle):
+    """(d) CGMY edges: Y in {0.99, 1.01, 1.99} (Gamma(-Y) poles at 1 and 2), M = alpha + 1 + 1e-9
+    (the Carr-Madan damping line touches the pole of the CF), small / large C and G."""
+    rows = []
+    for Y in (0.1, 0.99, 1.01, 1.99):
+        for M in (2.5 + 1e-9, 2.6, 15.0):
+            for G in (1.0, 15.0):
+                for C in (0.01, 2.0):
+                    rows.append([0.2, C, G, M, Y])
+                    rows.append([0.0, C, G, M, Y])
+    prm = np.array(rows)
+    # COS (three strikes of test.cpp:799 + the bench grid scaled to S0 = 500)
+    K = CASES.c5_strikes(500.0)
+    got = engine.cos(2, 0, prm, K, 500.0, .4, [.25, 1.0], 256, 1)
+    ref = best_oracle.cos(2, 0, prm, K, 500.0, .4, [.25, 1.0], 256, 1)
+    _, nbad = sweep_report(got, ref, prm, f"CGMY box edges COS puts {len(prm)}x2x66")
+    assert nbad == 0
+    # Carr-Madan N = 1024 (test.cpp:831), window of the reference's tests
+    N = 1024
+    got = engine.carr_madan(2, 0, prm, N, .25, 1.5, 500.0, .4, .25, True)
+    ref = best_oracle.carr_madan(2, 0, prm, N, .25, 1.5, 500.0, .4, .25, True)
+    lo, hi = int(N * .3), int(N * .7)
+    _, nbad = sweep_report(got[:, lo:hi], ref[:, lo:hi], prm, f"CGMY box edges Carr-Madan puts {len(prm)}x{hi - lo}")
+    assert nbad == 0
+
+
+def test_merton_box_edges_fsts_vs_oracle(engine, best_oracle):
+    """(d) Merton edges: lambda = 0 (no jumps), tiny / large jump size and intensity; one-step FSTS
+    (the reference's FSTSPrice) on N = 1024 and the COS pricer."""
+    rows = []
+    for lam in (0.0, 1e-6, 2.0):
+        for muJ in (-1.0, 0.5):
+            for sJ in (0.05, 1.5):
+                for sig in (0.05, 0.6):
+                    rows.append([sig, lam, muJ, sJ])
+    prm = np.array(rows)
+    got = engine.fsts(1, 0, prm, 1024, 5.0, 100.0, .05, 1.0, steps=1, american=False, payoff=1)
+    ref = best_oracle.fsts(1, 0, prm, 1024, 5.0, 100.0, .05, 1.0, steps=1, american=False, payoff=1)
+    _, nbad = sweep_report(got, ref, prm, f"Merton box edges FSTS puts {len(prm)}x1024")
+    assert nbad == 0
+    K, T = CASES.c5_strikes(), CASES.C5_T
+    got = engine.cos(1, 0, prm, K, 100.0, .05, T, 256, 0)
+    ref = best_oracle.cos(1, 0, prm, K, 100.0, .05, T, 256, 0)
+    _, nbad = sweep_report(got, ref, prm, f"Merton box edges COS calls {len(prm)}x8x66")
+    assert nbad == 0
+
+
+# ------------------------------------------------------------------------------------------------
+def test_american_put_literature_on_gpu_n32768_4096_steps(engine):
+    """External anchor of the (reference-less) American FSTS loop evaluated ON THE GPU:
+    Merton K=100 T=.25 r=.05 sigma=.15 lambda=.1 muJ=-.9 sigJ=.45 -> 10.003822 / 3.241251 /
+    1.419803 at S = 90/100/110 (d'Halluin, Forsyth, Labahn 2004), large-grid path N = 2^15, 4096
+    steps; SURVEY 8c: the restatement converges to 10.00375 / 3.24122 / 1.41980 there."""
+    p = [0.15, 0.1, -0.9, 0.45]
+    N, xmax = 32768, 7.5
+    v = engine.fsts(1, 0, p, N, xmax, 100.0, .05, .25, steps=4096, american=True, payoff=1)[0]
+    x = -xmax + (2.0 * xmax / (N - 1.0)) * np.arange(N)
+    from scipy.interpolate import CubicSpline
+    cs = CubicSpline(x, v)
+    for s, ref in [(90.0, 10.003822), (100.0, 3.241251), (110.0, 1.419803)]:
+        got = float(cs(math.log(s / 100.0)))
+        print(f"\n  American put S={s}: gpu {got:.6f} literature {ref:.6f} diff {got - ref:+.2e}")
+        assert abs(got - ref) < 2e-4
+
+
+@pytest.mark.parametrize("N", [1024, 4096, 16384])
+def test_fsts_one_step_loop_equals_fsts_price(N, engine, best_oracle):
+    """steps = 1, american = 0 IS the reference's FSTSPrice (OptionPricing.h:185-208): the time-loop
+    entry and the single-step entry must agree with the reference's one-step result."""
+    prm = CASES.merton_batch(4)
+    one = engine.fsts(1, 0, prm, N, 7.5, 100.0, .05, .25, steps=1, american=False, payoff=1)
+    ref = best_oracle.fsts(1, 0, prm, N, 7.5, 100.0, .05, .25, steps=1, american=False, payoff=1)
+    _, nbad = sweep_report(one, ref, prm, f"FSTS one step N={N}")
+    assert nbad == 0
