@@ -10,7 +10,8 @@ on): Heston (CIR-time-changed Brownian motion, generateCharts.cpp:231-250) COS c
 numU = 256, weak scaling with 125 000 parameter sets per GPU (8 GPUs = the 1e6-set sweep).
 One step = one pass over the rank's shard: every strike price is computed, written to HBM,
 reduced to the per-set weighted squared error against market quotes (fop_cos_loss), and for N > 1
-the per-set losses are all-gathered over NCCL.  A price counts once per (set, maturity, quoted
+the per-set losses are all-gathered through the library's own collective (fop_gather_losses_async:
+NCCL on a side stream, overlapped with the next step).  A price counts once per (set, maturity, quoted
 strike): 64 per row, although 66 are evaluated.
 
 Prints ONE JSON line (rank 0).  `value` = prices/s with inputs resident in HBM; `e2e` = the same
@@ -183,7 +184,9 @@ def load_ncu_summary():
     """Per-launch figures of the two hot kernels from the committed `ncu --set full` capture of this
     very command (profiles/README.md): DRAM bytes per launch, and for the coefficient kernel the
     executed fp64 operations per characteristic-function evaluation.  {} when absent."""
-    path = os.path.join(ROOT, "profiles", "r1_bench_top_kernels_ncu.json")
+    path = os.path.join(ROOT, "profiles", "r2_bench_top_kernels_ncu.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_bench_top_kernels_ncu.json")
     out = {}
 
     def num(s):
@@ -270,6 +273,78 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def extra_configs(eng, torch, dev, peak):
+    """The other BASELINE.json configs (C2, C3 at P = 4096, C4 at P = 16384) on one GPU, device
+    resident, timed per kernel with the library's CUDA-event profiling: driver-observed lines for
+    the kernels the headline workload does not touch.  Roofline per SURVEY.md 8d."""
+    import fftoptionpricing_b200 as F
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        fn()
+        eng.synchronize()
+        eng.profile_enable(True)
+        for _ in range(reps):
+            fn()
+        prof = eng.profile_read()
+        eng.profile_enable(False)
+        return {k: v[0] / reps for k, v in prof.items()}
+
+    # C2: Heston COS, 256 u x 1024 strikes, one maturity (batch of 4096 sets)
+    P = 4096
+    prm = torch.tensor(CASES.heston_batch(P), device=dev)
+    K = CASES.fang_oost_strikes(-5.0, 5.0, 100.0, 1024)
+    o = torch.empty((P, 1, 1024), dtype=torch.float64, device=dev)
+    k = timed(lambda: eng.cos(F.GAUSS, F.TC_CIR, prm, K, 100.0, 0.0, [1.0], 256, 0, out=o), 5)
+    ms = sum(k.values())
+    fl = P * 1024 * 4.0 * 256
+    out["C2"] = {"workload": f"Heston COS 256 u x 1024 strikes x {P} sets", "ms": ms, "kernels_ms": k,
+                 "value": P * 1024 / (ms * 1e-3), "unit": UNIT,
+                 "roofline": {"bound": "tensor", "algorithmic_flops": fl, "achieved": fl / (ms * 1e-3) / 1e12,
+                              "peak": peak, "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / peak,
+                              "what": "4 numU flops per price over the whole call (coefficient + contraction kernels)"}}
+    del o
+    # C3: Merton American put FSTS, N = 4096, 256 steps, 4096 sets
+    P = 4096
+    prm = torch.tensor(CASES.merton_batch(P), device=dev)
+    o = torch.empty((P, 4096), dtype=torch.float64, device=dev)
+    k = timed(lambda: eng.fsts(F.MERTON, 0, prm, 4096, 7.5, 100.0, .05, .25, steps=256, american=True,
+                               payoff=1, out=o), 3)
+    ms = sum(k.values())
+    fl = P * (256 * (2 * 5 * 4096 * 12 + 8 * 4096.0))
+    out["C3"] = {"workload": f"Merton American put FSTS 2^12 nodes x 256 steps x {P} sets", "ms": ms,
+                 "kernels_ms": k, "value": P * 4096 / (ms * 1e-3), "unit": UNIT,
+                 "roofline": {"bound": "tensor", "algorithmic_flops": fl, "achieved": fl / (ms * 1e-3) / 1e12,
+                              "peak": peak, "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / peak,
+                              "what": "steps x (2 x 5 N log2 N + 8 N) flops per set (SURVEY 8d)"}}
+    del o
+    # C4: CGMY Carr-Madan, N = 2^16, 16384 sets, all strikes (8 GiB of prices)
+    P = 16384
+    prm = torch.tensor(CASES.cgmy_batch(P), device=dev)
+    o = torch.empty((P, 65536), dtype=torch.float64, device=dev)
+    k = timed(lambda: eng.carr_madan(F.CGMY, 0, prm, 65536, .25, 1.5, 500.0, .4, .25, False, out=o), 3)
+    ms = sum(k.values())
+    by = P * 65536 * 8.0
+    hbm = measured_peaks().get("hbm_gbs", 6554.6)
+    out["C4"] = {"workload": f"CGMY Carr-Madan 2^16 points x {P} sets, all strikes", "ms": ms, "kernels_ms": k,
+                 "value": P * 65536 / (ms * 1e-3), "unit": UNIT,
+                 "roofline": {"bound": "hbm", "algorithmic_bytes": by, "achieved": by / (ms * 1e-3) / 1e9,
+                              "peak": hbm, "unit": "GB/s", "frac": by / (ms * 1e-3) / 1e9 / hbm,
+                              "what": "8 B per price written once (SURVEY 8d); 5 N log2 N accounting: %.2f TFLOP/s"
+                                      % (P * 5 * 65536 * 16 / (ms * 1e-3) / 1e12)}}
+    del o
+    torch.cuda.empty_cache()
+    return out
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -281,11 +356,17 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # torch.distributed is the launcher-side plumbing (rendezvous, barrier, max-over-ranks of
+        # the timings); the data-path collective is the library's own fop_gather_losses*
         dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     eng = F.Engine(local)
     stream = torch.cuda.ExternalStream(eng.stream_ptr, device=dev)
+    if world > 1:
+        box = [F.Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        eng.comm_init(box[0], rank, world)
 
     P = args.sets_per_gpu
     K, T = CASES.c5_strikes(S0), CASES.C5_T
@@ -294,26 +375,35 @@ def run_ours(args):
     # rank r prices the r-th contiguous slice of the global sweep (seeded synthetic inputs)
     prm_host = torch.from_numpy(CASES.heston_batch(P, seed=CASES.SEED + 1000 * rank)).pin_memory()
     loss_host = torch.empty(P, dtype=torch.float64).pin_memory()
+    gathered_host = torch.empty(P * world, dtype=torch.float64).pin_memory() if world > 1 else None
     prm_dev = prm_host.to(dev)
     prices = torch.empty((P, M, J), dtype=torch.float64, device=dev)
-    loss = torch.empty(P, dtype=torch.float64, device=dev)
-    gathered = torch.empty(P * world, dtype=torch.float64, device=dev) if world > 1 else None
+    # two (loss, gathered) buffer pairs alternate: the gather of step i runs beside step i + 1
+    loss = [torch.empty(P, dtype=torch.float64, device=dev) for _ in range(2)]
+    gathered = [torch.empty(P * world, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
     mkt_d = torch.from_numpy(mkt).to(dev)
     w_d = torch.from_numpy(w).to(dev)
 
-    def step_device():
-        eng.cos_loss(F.GAUSS, F.TC_CIR, prm_dev, K, S0, RATE, T, NUM_U, mkt_d, w_d, out=loss,
+    def step_device(i):
+        b = i & 1
+        eng.cos_loss(F.GAUSS, F.TC_CIR, prm_dev, K, S0, RATE, T, NUM_U, mkt_d, w_d, out=loss[b],
                      prices_out=prices)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, loss)
+            eng.gather_losses_async(loss[b], gathered[b])   # side stream, overlaps step i + 1
+
+    def finish_device():
+        if world > 1:
+            eng.comm_wait()
 
     def step_host():
         # host buffers in, host losses out: H2D of the parameter sets + D2H of the losses happen
-        # inside the call (which returns after the stream is idle)
         # inside the call (which returns after the stream is idle); prices are stored to HBM exactly
-        # as in the device-resident step
+        # as in the device-resident step; N > 1: the host losses go through the library's gather
+        # (H2D, NCCL all-gather, D2H of the full vector)
         eng.cos_loss(F.GAUSS, F.TC_CIR, prm_host.numpy(), K, S0, RATE, T, NUM_U, mkt, w,
                      out=loss_host.numpy(), prices_out=prices)
+        if world > 1:
+            eng.gather_losses(loss_host.numpy(), out=gathered_host.numpy())
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -321,22 +411,28 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
-            step_device()
-        barrier()
-        # ---- timed region: device-resident inputs
-        sampler = ClockSampler(local, str(getattr(torch.cuda.get_device_properties(local), 'uuid', '') or '')) if rank == 0 else None
-        l0 = eng.launch_count
+    def timed_device(nsteps):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
-        for _ in range(args.steps):
-            step_device()
+        for i in range(nsteps):
+            step_device(i)
+        finish_device()
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
+        return e0.elapsed_time(e1)
+
+    uuid = str(getattr(torch.cuda.get_device_properties(local), "uuid", "") or "")
+    with torch.cuda.stream(stream):
+        for i in range(max(args.warmup, 3)):
+            step_device(i)
+        finish_device()
+        barrier()
+        # ---- timed region: device-resident inputs
+        sampler = ClockSampler(local, uuid) if rank == 0 else None
+        l0 = eng.launch_count
+        ms = timed_device(args.steps)
         launches = eng.launch_count - l0
 
         # ---- end to end through the C ABI with host buffers
@@ -346,29 +442,70 @@ def run_ours(args):
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step_host()
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, loss_host.to(dev, non_blocking=True))
         barrier()
         e2e_s = time.perf_counter() - t0
         clocks = sampler.stop() if sampler else None   # sampled over both timed regions
 
+        # ---- sustained leg: the same device-resident step for >= args.sustain_seconds
+        sustained = None
+        if args.sustain_seconds > 0:
+            n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms / args.steps, 1e-3)) + 1)
+            sampler2 = ClockSampler(local, uuid) if rank == 0 else None
+            ms_sus = timed_device(n_sus)
+            clocks2 = sampler2.stop() if sampler2 else None
+            sustained = (n_sus, ms_sus, clocks2)
+
         # ---- per-kernel timing for the roofline (separate pass so events do not perturb `value`)
         eng.profile_enable(True)
         for _ in range(args.steps):
-            eng.cos_loss(F.GAUSS, F.TC_CIR, prm_dev, K, S0, RATE, T, NUM_U, mkt_d, w_d, out=loss,
+            eng.cos_loss(F.GAUSS, F.TC_CIR, prm_dev, K, S0, RATE, T, NUM_U, mkt_d, w_d, out=loss[0],
                          prices_out=prices)
         prof = eng.profile_read()
         eng.profile_enable(False)
         peaks = eng.microbench_fp64() if rank == 0 else None
 
+        # ---- N = 1 only: strong-scaling anchor (the fixed 1e6-set sweep on one GPU) + other configs
+        strong = None
+        extra = None
+        if world == 1 and not args.no_extra:
+            del prices
+            torch.cuda.empty_cache()
+            Pg = args.sets_per_gpu * 8
+            prm_g = torch.tensor(CASES.heston_batch(Pg), device=dev)
+            loss_g = torch.empty(Pg, dtype=torch.float64, device=dev)
+            prices_g = torch.empty((Pg, M, J), dtype=torch.float64, device=dev)
+
+            def big():
+                eng.cos_loss(F.GAUSS, F.TC_CIR, prm_g, K, S0, RATE, T, NUM_U, mkt_d, w_d, out=loss_g,
+                             prices_out=prices_g)
+            big()
+            big()
+            torch.cuda.synchronize(dev)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                big()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            ms_g = e0.elapsed_time(e1) / 5
+            strong = {"what": f"the fixed {Pg}-set sweep (the 8-GPU job) on ONE GPU, device resident: the "
+                              "strong-scaling anchor for the per-N weak-scaling values",
+                      "global_sets": Pg, "ms_per_step": ms_g, "value": Pg * M * COUNTED_STRIKES / (ms_g * 1e-3),
+                      "unit": UNIT}
+            del prm_g, loss_g, prices_g
+            torch.cuda.empty_cache()
+            extra = extra_configs(eng, torch, dev, max(peaks[0], peaks[1]))
+
     # max over ranks
-    t = torch.tensor([ms, e2e_s * 1e3, float(launches)], dtype=torch.float64, device=dev)
+    sus_ms = sustained[1] if sustained else 0.0
+    t = torch.tensor([ms, e2e_s * 1e3, float(launches), sus_ms], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, e2e_ms, launches = float(tmax[0]), float(tmax[1]), int(tsum[2])
+        ms, e2e_ms, launches, sus_ms = float(tmax[0]), float(tmax[1]), int(tsum[2]), float(tmax[3])
     else:
         ms, e2e_ms = float(t[0]), float(t[1])
 
@@ -380,68 +517,85 @@ def run_ours(args):
         gemm_ms, gemm_n = prof.get("cos_gemm_kernel", (0.0, 0))
         coef_ms, coef_n = prof.get("cos_coeff_kernel", (0.0, 0))
         peak = max(peaks[0], peaks[1])
-        # algorithmic flops of the contraction: 4*numU per evaluated price
-        gemm_flops_per_launch = rows * J * 4.0 * NUM_U / max(gemm_n / args.steps, 1)
-        gemm_avg_s = gemm_ms * 1e-3 / max(gemm_n, 1)
-        achieved = gemm_flops_per_launch / gemm_avg_s / 1e12 if gemm_n else None
-        ncu = load_ncu_summary()
-        gemm_traffic = ncu.get("cos_gemm_kernel", {}).get("dram_bytes")
+        step_ms = ms / args.steps
         step_kernel_ms = max(sum(v[0] for v in prof.values()), 1e-9)
-        tensor_note = ("fp64 pipe, 64 FMA/clk/SM: mma.sync.m8n8k4.f64 (DMMA) and DFMA share it; "
-                       "tcgen05/TMEM have no f64 kind")
+        ncu = load_ncu_summary()
+        pipe_note = ("fp64 pipe, 64 FMA/clk/SM: mma.sync.m8n8k4.f64 (DMMA) and DFMA share it; "
+                     "tcgen05/TMEM have no f64 kind")
         peak_note = ("fp64 throughput measured live in this process (fop_microbench_fp64: DFMA %.1f, "
                      "DMMA m8n8k4 %.1f TFLOP/s); MEASURED_PEAKS.json has no fp64 entry"
                      % (peaks[0], peaks[1]))
-        # second hot kernel: CF evaluation has no algorithmic flop count in SURVEY 8d (reported as
-        # cf_evals); its fraction is executed fp64 flops (ncu instruction counts per evaluation,
-        # committed under profiles/) over the same measured peak
+        # SURVEY 8d algorithmic flops of the step: 4 numU per evaluated price (the contraction); the
+        # characteristic-function evaluations carry none by that definition and are reported through
+        # their executed fp64 flop count (ncu instruction counts, committed under profiles/)
+        step_flops = rows * J * 4.0 * NUM_U
         evals_per_step = P * M * NUM_U
         coef_flops = ncu.get("cos_coeff_kernel", {}).get("fp64_flops_per_cf_eval")
-        coef_ach = (coef_flops * evals_per_step * args.steps / (coef_ms * 1e-3) / 1e12
+        gemm_launches_per_step = max(gemm_n / args.steps, 1)
+        coef_launches_per_step = max(coef_n / args.steps, 1)
+        gemm_avg_s = gemm_ms * 1e-3 / max(gemm_n, 1)
+        coef_avg_s = coef_ms * 1e-3 / max(coef_n, 1)
+        gemm_ach = step_flops / gemm_launches_per_step / gemm_avg_s / 1e12 if gemm_n else None
+        coef_ach = (coef_flops * evals_per_step / coef_launches_per_step / coef_avg_s / 1e12
                     if coef_flops and coef_n else None)
+        gemm_entry = {
+            "kernel": "cos_gemm_kernel", "bound": "tensor", "pipe": pipe_note, "achieved": gemm_ach,
+            "peak": peak, "unit": "TFLOP/s", "frac": (gemm_ach / peak) if gemm_ach else None,
+            "traffic": ncu.get("cos_gemm_kernel", {}).get("dram_bytes"),
+            "algorithmic_flops_per_launch": step_flops / gemm_launches_per_step,
+            "algorithmic_bytes_per_launch": rows * (2.0 * NUM_U * 8 + J * 8) / gemm_launches_per_step,
+            "avg_launch_ms": gemm_avg_s * 1e3, "share_of_step": gemm_ms / step_kernel_ms}
+        coef_entry = {
+            "kernel": "cos_coeff_kernel", "bound": "tensor", "pipe": "fp64 pipe (DFMA/DMUL/DADD), dispatch-bound: "
+            "an fp64 warp instruction occupies the dispatch port for two cycles (profiles/r2_coeff_variants.json)",
+            "achieved": coef_ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": (coef_ach / peak) if coef_ach else None,
+            "traffic": ncu.get("cos_coeff_kernel", {}).get("dram_bytes"),
+            "what": "executed fp64 flops per CF evaluation (ncu instruction counts of the shipped kernel, "
+                    "profiles/) x evaluations per launch / launch time; SURVEY 8d assigns CF evaluation no "
+                    "algorithmic flops, so the step-level fraction below is the conservative figure",
+            "fp64_flops_per_cf_eval": coef_flops, "cf_evals_per_launch": evals_per_step / coef_launches_per_step,
+            "avg_launch_ms": coef_avg_s * 1e3, "share_of_step": coef_ms / step_kernel_ms}
+        dominant, other = (coef_entry, gemm_entry) if coef_ms >= gemm_ms else (gemm_entry, coef_entry)
+        roofline = dict(dominant)
+        roofline["peak_source"] = peak_note
+        roofline["whole_step"] = {
+            "achieved": step_flops / (step_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+            "frac": step_flops / (step_ms * 1e-3) / 1e12 / peak,
+            "what": "SURVEY 8d algorithmic flops of the step (4 numU per evaluated price; CF evaluation not "
+                    "counted) over the whole step time"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(P, world),
             "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": int(prm_host.numel() * 8 + (J + M + 2 * M * J) * 8),
-                    "d2h_bytes_per_step": int(P * 8), "ms_per_step": e2e_ms / args.steps,
-                    "what": "fop_cos_loss with host parameter sets in / host losses out"},
+                    "h2d_bytes_per_step": int(prm_host.numel() * 8 + (J + M + 2 * M * J) * 8
+                                              + (P * 8 if world > 1 else 0)),
+                    "d2h_bytes_per_step": int(P * 8 + (P * world * 8 if world > 1 else 0)),
+                    "ms_per_step": e2e_ms / args.steps,
+                    "what": "fop_cos_loss with host parameter sets in / host losses out"
+                            + (" + fop_gather_losses on the host loss vectors" if world > 1 else "")},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {
-                "bound": "tensor", "pipe": tensor_note, "kernel": "cos_gemm_kernel",
-                "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": gemm_traffic,
-                "peak_source": peak_note,
-                "algorithmic_flops_per_launch": gemm_flops_per_launch,
-                "algorithmic_bytes_per_launch": rows * (2.0 * NUM_U * 8 + J * 8) / max(gemm_n / args.steps, 1),
-                "avg_launch_ms": gemm_avg_s * 1e3,
-                "share_of_step": gemm_ms / step_kernel_ms,
-            },
-            "roofline_other": [
-                {"kernel": "cos_coeff_kernel", "bound": "tensor", "pipe": "fp64 pipe (DFMA/DMUL/DADD)",
-                 "achieved": coef_ach, "peak": peak, "unit": "TFLOP/s",
-                 "frac": (coef_ach / peak) if coef_ach else None,
-                 "what": "executed fp64 flops per CF evaluation (ncu, profiles/) x evaluations / s; "
-                         "SURVEY 8d counts no algorithmic flops for CF evaluation",
-                 "fp64_flops_per_cf_eval": coef_flops,
-                 "avg_launch_ms": coef_ms / max(coef_n, 1), "share_of_step": coef_ms / step_kernel_ms,
-                 "traffic": ncu.get("cos_coeff_kernel", {}).get("dram_bytes")},
-                {"kernel": "whole step", "bound": "tensor",
-                 "achieved": rows * J * 4.0 * NUM_U / (ms / args.steps * 1e-3) / 1e12, "peak": peak,
-                 "unit": "TFLOP/s",
-                 "frac": rows * J * 4.0 * NUM_U / (ms / args.steps * 1e-3) / 1e12 / peak,
-                 "what": "SURVEY 8d algorithmic flops (4 numU per evaluated price, CF evaluation "
-                         "not counted) over the whole step time"},
-            ],
+            "roofline": roofline,
+            "roofline_other": [other],
             "kernels": {
                 k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
                 for k, v in prof.items()},
             "cf_evals_per_s": (P * M * NUM_U * args.steps / (coef_ms * 1e-3)) if coef_n else None,
+            "collective": ("fop_gather_losses_async (the library's NCCL all-gather) on a side stream, overlapped "
+                           "with the next step" if world > 1 else None),
         }
+        if sustained:
+            n_sus = sustained[0]
+            line["sustained"] = {"seconds": sus_ms * 1e-3, "steps": n_sus, "ms_per_step": sus_ms / n_sus,
+                                 "value": prices_per_step * n_sus / (sus_ms * 1e-3), "unit": UNIT,
+                                 "clocks": sustained[2]}
+        if strong:
+            line["strong_scaling_anchor"] = strong
+        if extra:
+            line["extra_configs"] = extra
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_rate(args.cpu_seconds).items()
                                     if k in ("value", "unit", "cores", "kind", "sample")}
@@ -473,6 +627,10 @@ def main():
     ap.add_argument("--sets-per-gpu", type=int, default=SETS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sustain-seconds", type=float, default=3.0,
+                    help="length of the sustained leg (0 disables it)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the N=1-only strong-scaling anchor and the C2/C3/C4 lines")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -64,10 +64,23 @@ _SIGNATURES = {
     "fop_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fop_comm_init": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int]),
     "fop_gather_losses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fop_gather_losses_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fop_comm_wait": (C.c_int, [C.c_void_p]),
     "fop_comm_destroy": (C.c_int, [C.c_void_p]),
     "fop_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "fop_integrate_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_double, C.c_int, C.c_void_p]),
+    "fop_cos_u_grid": (C.c_int, [_dp, C.c_int, C.c_double, C.c_int, _dp]),
+    "fop_cos_cf_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double,
+                                     C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fop_carr_madan_u_grid": (C.c_int, [C.c_int, C.c_double, C.c_double, _dp]),
+    "fop_carr_madan_cf_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                            C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                                            C.c_void_p]),
+    "fop_fsts_u_grid": (C.c_int, [C.c_int, C.c_double, _dp]),
+    "fop_fsts_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                   C.c_int, C.c_void_p]),
     "fop_measure_fp64_peak": (C.c_int, [C.c_void_p, _dp]),
 }
 # not part of the public header: tuning probe used by profiles/ scripts

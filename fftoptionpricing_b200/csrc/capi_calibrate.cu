@@ -184,9 +184,13 @@ extern "C" int fop_calibrate_cf(fop_handle_t h, fop_model_t model, const double*
     return fail(h, FOP_INVALID_ARG,
                 "fop_calibrate_cf: need 1 <= m <= 2048, 2 <= nests <= %d, iterations >= 0, restarts >= 1",
                 CK_MAX_NESTS);
-  for (int i = 0; i < np; ++i)
-    if (!(upper[i] >= lower[i])) return fail(h, FOP_INVALID_ARG, "bound %d: upper < lower", i);
   FOP_CUDA(h, cudaSetDevice(h->device));
+  // the bounds may be host or device pointers like every other array argument: validate a host copy
+  double lo_h[16], hi_h[16];
+  FOP_CUDA(h, cudaMemcpy(lo_h, lower, (size_t)np * 8, cudaMemcpyDefault));
+  FOP_CUDA(h, cudaMemcpy(hi_h, upper, (size_t)np * 8, cudaMemcpyDefault));
+  for (int i = 0; i < np; ++i)
+    if (!(hi_h[i] >= lo_h[i])) return fail(h, FOP_INVALID_ARG, "bound %d: upper < lower", i);
   Arena ar(h);
   FOP_TRY(ar.reserve(2 * Arena::pad((size_t)np * 8) + stage_bytes(u, (size_t)m * 8) +
                      stage_bytes(phiHat, (size_t)m * 16) + Arena::pad((size_t)restarts * np * 8) +

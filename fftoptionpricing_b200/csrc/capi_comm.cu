@@ -107,7 +107,45 @@ int fop_gather_losses(fop_handle_t h, const double* loss_local, int count, doubl
   if (r != 0) return nccl_fail(h, "ncclAllGather", r);
   if (out_host)
     FOP_CUDA(h, cudaMemcpyAsync(loss_all, dst, (size_t)count * world * 8, cudaMemcpyDeviceToHost, h->stream));
-  FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+  // device output: enqueue only (include/fftop_b200.h conventions); host output: return when it is there
+  if (out_host) FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FOP_OK;
+}
+
+int fop_gather_losses_async(fop_handle_t h, const double* loss_local, int count, double* loss_all) {
+  if (!h) return FOP_INVALID_ARG;
+  if (!h->comm) return fail(h, FOP_INVALID_ARG, "fop_gather_losses_async: call fop_comm_init first");
+  if (!loss_local || !loss_all || count < 0) return fail(h, FOP_INVALID_ARG, "null pointer / negative count");
+  if (!is_device_ptr(loss_local) || !is_device_ptr(loss_all))
+    return fail(h, FOP_INVALID_ARG, "fop_gather_losses_async takes device pointers (host buffers: fop_gather_losses)");
+  if (count == 0) return FOP_OK;
+  NcclApi& a = nccl();
+  FOP_CUDA(h, cudaSetDevice(h->device));
+  if (!h->comm_stream) {
+    FOP_CUDA(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    FOP_CUDA(h, cudaEventCreateWithFlags(&h->comm_ready, cudaEventDisableTiming));
+    FOP_CUDA(h, cudaEventCreateWithFlags(&h->comm_done, cudaEventDisableTiming));
+  }
+  // Kernels enqueued after this call may overwrite the buffers of the PREVIOUS async gather (two
+  // buffer pairs alternate), so the handle's stream first waits for that one -- it has had a whole
+  // step to finish.  The new gather starts when everything enqueued so far on the handle's stream
+  // (the loss kernel) is done, and runs beside whatever the caller enqueues next.
+  if (h->comm_pending) FOP_CUDA(h, cudaStreamWaitEvent(h->stream, h->comm_done, 0));
+  FOP_CUDA(h, cudaEventRecord(h->comm_ready, h->stream));
+  FOP_CUDA(h, cudaStreamWaitEvent(h->comm_stream, h->comm_ready, 0));
+  const ncclResult_t r = a.AllGather(loss_local, loss_all, (size_t)count, ncclFloat64,
+                                     static_cast<ncclComm_t>(h->comm), h->comm_stream);
+  if (r != 0) return nccl_fail(h, "ncclAllGather", r);
+  FOP_CUDA(h, cudaEventRecord(h->comm_done, h->comm_stream));
+  h->comm_pending = true;
+  return FOP_OK;
+}
+
+int fop_comm_wait(fop_handle_t h) {
+  if (!h) return FOP_INVALID_ARG;
+  if (!h->comm_pending) return FOP_OK;
+  FOP_CUDA(h, cudaStreamWaitEvent(h->stream, h->comm_done, 0));
+  h->comm_pending = false;
   return FOP_OK;
 }
 
@@ -117,6 +155,15 @@ int fop_comm_destroy(fop_handle_t h) {
   NcclApi& a = nccl();
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->comm_stream) {
+    cudaStreamSynchronize(h->comm_stream);
+    cudaEventDestroy(h->comm_ready);
+    cudaEventDestroy(h->comm_done);
+    cudaStreamDestroy(h->comm_stream);
+    h->comm_stream = nullptr;
+    h->comm_ready = h->comm_done = nullptr;
+    h->comm_pending = false;
+  }
   if (a.ok) a.CommDestroy(static_cast<ncclComm_t>(h->comm));
   h->comm = nullptr;
   h->comm_world = 0;

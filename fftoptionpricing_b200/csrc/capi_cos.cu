@@ -15,6 +15,8 @@ namespace fop {  // capi_cos_fused.cu
 int cos_fused_pick_nb(int J);
 int cos_fused_consts(fop_handle_t h, int base, int tc, const double* params, int np, int P, ModelConsts* out);
 int cos_fused_launch(fop_handle_t h, CosFusedArgs& a, int NB);
+// capi_cos_coeff.cu
+bool cos_coeff_launch_spec(fop_handle_t h, const CosCoeffArgs& a, int grid_blocks_per_sm);
 }  // namespace fop
 
 namespace {
@@ -50,13 +52,17 @@ const GemmVariant* pick_gemm(int J, int* nblk_out) {
 }
 
 // kinds[nk]: output kinds (fop_cos_kind); out = [nk][P][M][J] (or nullptr in loss-only mode)
+// cf_samples != nullptr: the characteristic function is given by its samples phi_{p,m}(i u_k)
+// ([P][M][numU][2], fop_cos_cf_samples) instead of (model, params)
 int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, const double* K_desc,
             int J, double S0, double r, const double* T, int M, int numU, const int* kinds, int nk,
-            const double* mkt, const double* w, double* out, double* loss) {
+            const double* mkt, const double* w, double* out, double* loss,
+            const double* cf_samples = nullptr) {
   if (!h) return FOP_INVALID_ARG;
-  const int np = num_params(model.base, model.time_change);
-  if (np == 0) return fail(h, FOP_INVALID_ARG, "unknown model (%d,%d)", model.base, model.time_change);
-  if (!params || !K_desc || !T) return fail(h, FOP_INVALID_ARG, "null input pointer");
+  const int np = cf_samples ? 0 : num_params(model.base, model.time_change);
+  if (!cf_samples && np == 0)
+    return fail(h, FOP_INVALID_ARG, "unknown model (%d,%d)", model.base, model.time_change);
+  if ((!params && !cf_samples) || !K_desc || !T) return fail(h, FOP_INVALID_ARG, "null input pointer");
   if (!out && !loss) return fail(h, FOP_INVALID_ARG, "no output requested");
   if (P < 0 || J < 2 || M < 1 || numU < 1 || numU > 16384 || !kinds || nk < 1 || nk > 8)
     return fail(h, FOP_INVALID_ARG, "bad sizes P=%d J=%d M=%d numU=%d nkinds=%d", P, J, M, numU, nk);
@@ -83,7 +89,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const int spt = M <= FW_MAX_M ? FW_ROWS / M : 0;
   bool fused = false;
   if (const char* force = std::getenv("FOP_COS_PATH"))
-    fused = !std::strcmp(force, "fused") && nk == 1 && fnb > 0 && spt > 0;
+    fused = !std::strcmp(force, "fused") && nk == 1 && fnb > 0 && spt > 0 && !cf_samples;
   const GemmExVariant* gx = fused ? nullptr : pick_gemm_ex(J);
   if (fused || gx) nblk = 1;
   const int JB = fused ? 8 * fnb : gx ? 8 * gx->NB : 8 * gv->NB;
@@ -118,12 +124,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     std::copy(Th.begin(), Th.end(), x + 2 * J);
     cc.dt = 0.0;
     std::vector<int> npow;
-    if (maturity_grid(Th, &cc.dt, &npow) && !std::getenv("FOP_COS_NO_TGRID")) {
-      const std::vector<int> steps = maturity_steps(npow);
-      std::memcpy(tab.data() + npow_off, steps.data(), sizeof(int) * M);
-    }
-    else
-      cc.dt = 0.0;
+    std::vector<int> steps;
+    if (maturity_grid(Th, &cc.dt, &npow) && !std::getenv("FOP_COS_NO_TGRID")) steps = maturity_steps(npow);
+    if (!steps.empty()) std::memcpy(tab.data() + npow_off, steps.data(), sizeof(int) * M);
+    else cc.dt = 0.0;
     const double xMin = x[0], xMax = x[J - 1];
     const double du = M_PI / (xMax - xMin), cp = 2.0 / (xMax - xMin);
     for (int k = 0; k < numU; ++k) {
@@ -173,7 +177,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const int lossblk = nblk;
 
   Arena ar(h);
-  size_t need = stage_bytes(params, (size_t)P * np * 8);
+  size_t need = cf_samples ? stage_bytes(cf_samples, (size_t)P * M * numU * 16) : stage_bytes(params, (size_t)P * np * 8);
   if (mkt) need += stage_bytes(mkt, (size_t)M * J * 8);
   if (w) need += stage_bytes(w, (size_t)M * J * 8);
   need += fused ? Arena::pad((size_t)P * sizeof(ModelConsts)) : Arena::pad((size_t)chunk_rows * KK * 8 * ngreeks);
@@ -182,7 +186,9 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   FOP_TRY(ar.reserve(need));
 
   const double *d_params = nullptr, *d_mkt = nullptr, *d_w = nullptr;
-  FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
+  const double* d_phi = nullptr;
+  if (cf_samples) FOP_TRY(stage_in(h, ar, cf_samples, (size_t)P * M * numU * 2, &d_phi));
+  else FOP_TRY(stage_in(h, ar, params, (size_t)P * np, &d_params));
   if (mkt) FOP_TRY(stage_in(h, ar, mkt, (size_t)M * J, &d_mkt));
   if (w) FOP_TRY(stage_in(h, ar, w, (size_t)M * J, &d_w));
   double* d_C = fused ? nullptr : ar.alloc<double>((size_t)chunk_rows * KK * ngreeks);
@@ -229,7 +235,19 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
                                     h->stream));
       continue;
     }
-    {
+    if (cf_samples) {
+      CosSampleArgs sa;
+      sa.greek_mask = greek_mask;  sa.plane = (size_t)rows * KK;  sa.rows = rows;
+      sa.K = numU;  sa.Kp = KK / 2;  sa.r = r;
+      sa.phi = d_phi + (size_t)p0 * M * numU * 2;
+      sa.uk = d_tab;  sa.vk = d_tab + numU;  sa.C = d_C;
+      const long long n = rows * sa.Kp;
+      {
+        ProfScope ps(h, "cos_coeff_samples_kernel");
+        cos_coeff_samples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(sa);
+      }
+      FOP_LAUNCH_CHECK(h);
+    } else {
       CosCoeffArgs ca;
       ca.base = model.base;  ca.tc = model.time_change;
       ca.greek_mask = greek_mask;  ca.plane = (size_t)rows * KK;
@@ -242,10 +260,13 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       const int cgrid = std::min(ngroups, h->sm_count * 32);
       {
         ProfScope ps(h, "cos_coeff_kernel");
-        int ilp = M >= 2 ? 2 : 1;  // measured: 2 maturities interleaved beat 1 and 4 (register cap 128)
-        if (const char* e = std::getenv("FOP_COEFF_ILP")) ilp = std::max(1, std::min(atoi(e), M >= 2 ? 2 : 1));
-        if (ilp >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
-        else cos_coeff_kernel<1><<<cgrid, 256, 0, h->stream>>>(ca);
+        // default: model-specialised kernel (capi_cos_coeff.cu); FOP_COEFF_GENERIC=1: the generic one
+        if (std::getenv("FOP_COEFF_GENERIC") || !cos_coeff_launch_spec(h, ca, 32)) {
+          int ilp = M >= 2 ? 2 : 1;
+          if (const char* e = std::getenv("FOP_COEFF_ILP")) ilp = std::max(1, std::min(atoi(e), M >= 2 ? 2 : 1));
+          if (ilp >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
+          else cos_coeff_kernel<1><<<cgrid, 256, 0, h->stream>>>(ca);
+        }
       }
       FOP_LAUNCH_CHECK(h);
     }
@@ -296,6 +317,24 @@ int fop_cos(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   if (h && !out) return fop::fail(h, FOP_INVALID_ARG, "null output pointer");
   return cos_run(h, model, params, P, K_desc, J, S0, r, T, M, numU, &kind, 1, nullptr, nullptr, out,
                  nullptr);
+}
+
+int fop_cos_u_grid(const double* K_desc, int J, double S0, int numU, double* u_out) {
+  if (!K_desc || !u_out || J < 2 || numU < 1) return FOP_INVALID_ARG;
+  // u_k = k pi / (x_max - x_min), x = log(S0 / K)  (getXFromK OptionPricing.h:110-117; the grid of
+  // fangoost::computeExpectationVectorLevy)
+  const double xMin = std::log(S0 / K_desc[0]), xMax = std::log(S0 / K_desc[J - 1]);
+  const double du = M_PI / (xMax - xMin);
+  for (int k = 0; k < numU; ++k) u_out[k] = du * k;
+  return FOP_OK;
+}
+
+int fop_cos_cf_samples(fop_handle_t h, const double* cf_samples, int P, const double* K_desc, int J,
+                       double S0, double r, const double* T, int M, int numU, int kind, double* out) {
+  if (h && (!out || !cf_samples)) return fop::fail(h, FOP_INVALID_ARG, "null pointer");
+  const fop_model_t none = {0, 0};
+  return cos_run(h, none, nullptr, P, K_desc, J, S0, r, T, M, numU, &kind, 1, nullptr, nullptr, out,
+                 nullptr, cf_samples);
 }
 
 int fop_cos_greeks(fop_handle_t h, fop_model_t model, const double* params, int P,

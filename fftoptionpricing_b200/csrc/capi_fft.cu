@@ -7,18 +7,9 @@
 
 #include "cf_models.cuh"
 #include "fft_engine.cuh"
+#include "fft_run.cuh"
 #include "handle.cuh"
 
-namespace {
-using namespace fop;
-
-int ilog2(int N) {
-  int n = 0;
-  while ((1 << n) < N) ++n;
-  return n;
-}
-
-}  // namespace
 namespace fop {
 // cached exact twiddle table e^{-2 pi i k/N} (also used by capi_fsts.cu)
 int get_twiddles_shared(fop_handle_t h, int N, const double2** out) {
@@ -37,22 +28,6 @@ int get_twiddles_shared(fop_handle_t h, int N, const double2** out) {
 }
 }  // namespace fop
 namespace {
-inline int get_twiddles(fop_handle_t h, int N, const double2** out) { return fop::get_twiddles_shared(h, N, out); }
-
-// ---- generic load / store functors (fop_fft)
-struct LoadGen {
-  static constexpr bool has_cf = false;
-  static size_t aux_bytes(int) { return 0; }
-  const cd* data;
-  int N;
-  __device__ void prepare(void*, int, int) const {}
-  __device__ cd operator()(const void*, int, int p, int j) const { return data[(size_t)p * N + j]; }
-};
-struct StoreEpi {
-  cd* data;
-  int N;
-  __device__ void operator()(int p, int k, cd v) const { data[(size_t)p * N + k] = v; }
-};
 // direct O(N^2) transform for N < 16 (one thread per output)
 __global__ void tiny_dft_kernel(cd* data, int batch, int N, int sign) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,62 +290,6 @@ struct IntEpi {
   }
 };
 
-// runs `batch` transforms of length N through the engine
-template <int SIGN, typename Gen, typename Epi>
-int run_fft(fop_handle_t h, Arena& ar, int N, int batch, Gen gen, Epi epi) {
-  const int n = ilog2(N);
-  if (n <= 13) {
-    const double2* tw = nullptr;
-    FOP_TRY(get_twiddles(h, N, &tw));
-    const size_t smem = fft_single_smem(n) + Gen::aux_bytes(fft_single_tpb(n));
-    auto kern = fft_single_kernel<SIGN, Gen, Epi>;
-    FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tpb = fft_single_tpb(n);
-    const int groups = (batch + tpb - 1) / tpb;
-    const int grid = std::min(groups, h->sm_count * 8);
-    {
-      ProfScope ps(h, Gen::has_cf ? "carr_madan_single_kernel" : "fft_single_kernel");
-      kern<<<grid, fft_single_threads(n), smem, h->stream>>>(n, batch, tw, gen, epi);
-    }
-    FOP_LAUNCH_CHECK(h);
-    return FOP_OK;
-  }
-  const FourStep f = four_step_plan(n);
-  const int N1 = 1 << f.n1, N2 = 1 << f.n2;
-  const double2 *tw1 = nullptr, *tw2 = nullptr, *twN = nullptr;
-  FOP_TRY(get_twiddles(h, N1, &tw1));
-  FOP_TRY(get_twiddles(h, N2, &tw2));
-  FOP_TRY(get_twiddles(h, N, &twN));
-  // scratch for up to `pb` transforms in flight (<= 512 MiB)
-  const int pb = (int)std::max<long long>(1, std::min<long long>(batch, (512ll << 20) / ((long long)N * 16)));
-  cd* scratch = ar.alloc<cd>((size_t)pb * N);
-  if (!scratch) return fail(h, FOP_OOM, "arena exhausted for four-step scratch");
-  auto ka = fft_cols_kernel<SIGN, Gen>;
-  auto kb = fft_rows_kernel<SIGN, Epi>;
-  const size_t sa = four_step_smem(f.n1, f.ta) + Gen::aux_bytes(1), sb = four_step_smem(f.n2, f.tb);
-  FOP_CUDA(h, cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa));
-  FOP_CUDA(h, cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb));
-  for (int p0 = 0; p0 < batch; p0 += pb) {
-    const int pc = std::min(pb, batch - p0);
-    {
-      ProfScope ps(h, Gen::has_cf ? "carr_madan_cols_kernel" : "fft_cols_kernel");
-      ka<<<dim3(N2 / f.ta, pc), f.ta * (N1 / 16), sa, h->stream>>>(f, p0, tw1, twN, gen, scratch);
-    }
-    FOP_LAUNCH_CHECK(h);
-    {
-      ProfScope ps(h, Gen::has_cf ? "carr_madan_rows_kernel" : "fft_rows_kernel");
-      kb<<<dim3(N1 / f.tb, pc), f.tb * (N2 / 16), sb, h->stream>>>(f, p0, tw2, scratch, epi);
-    }
-    FOP_LAUNCH_CHECK(h);
-  }
-  return FOP_OK;
-}
-size_t fft_scratch_bytes(int N, int batch) {
-  if (ilog2(N) <= 13) return 0;
-  const long long pb = std::max<long long>(1, std::min<long long>(batch, (512ll << 20) / ((long long)N * 16)));
-  return Arena::pad((size_t)pb * N * 16);
-}
-
 }  // namespace
 
 namespace {
@@ -570,11 +489,22 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
   const bool out_host = !is_device_ptr(out);
   // host-bound outputs are produced in chunks of <= 1 GiB of device staging
   const long long chunkP = out_host ? std::max<long long>(1, std::min<long long>(P, (1ll << 30) / ((long long)N * 8))) : P;
-  // the pruned path of long grids needs head buffers (<= 512 MiB) next to the transform scratch of
-  // its longer heads (<= 512 MiB) and two routing index arrays
-  const size_t prune_bytes = N > 8192 ? (size_t)(512ll << 20) + Arena::pad((size_t)(512ll << 20)) +
-                                            2 * Arena::pad((size_t)chunkP * 4)
-                                      : 0;
+  const bool no_skip = std::getenv("FOP_CM_NO_SKIP") != nullptr;
+  // long grids of a Levy model: route the sets whose non-zero head fits a single-CTA transform
+  // through the input-pruned path (FOP_CM_NO_PRUNE=1: A/B runs)
+  const bool try_prune = N > 8192 && model.time_change == FOP_TC_NONE && !no_skip &&
+                         !std::getenv("FOP_CM_NO_PRUNE");
+  // the pruned path needs head buffers (sized from the real work, <= 512 MiB), the transform scratch
+  // of its 2^14 / 2^15-point heads, and two routing index arrays -- nothing when it is not taken
+  size_t prune_bytes = 0;
+  if (try_prune) {
+    const long long Lmax = std::min<long long>(32768, N / 2);
+    const long long head = std::min<long long>(chunkP * Lmax * 16, 512ll << 20);
+    const long long tb = std::max<long long>(1, head / (Lmax * 16));
+    prune_bytes = Arena::pad((size_t)head) +
+                  fft_scratch_bytes((int)Lmax, (int)std::min<long long>(tb * (N / Lmax) / 2 + 1, 1 << 30)) +
+                  2 * Arena::pad((size_t)chunkP * 4);
+  }
   Arena ar(h);
   FOP_TRY(ar.reserve(stage_bytes(params, (size_t)P * np * 8) +
                      (out_host ? Arena::pad((size_t)chunkP * N * 8) : 0) +
@@ -585,11 +515,6 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
   const double b = M_PI / ada;        // getMaxK,  OptionPricing.h:31-33
   const double lambda = 2.0 * b / N;  // getLambda, :40-42
   const double discount = std::exp(-r * T);
-  const bool no_skip = std::getenv("FOP_CM_NO_SKIP") != nullptr;
-  // long grids of a Levy model: route the sets whose non-zero head fits a single-CTA transform
-  // through the input-pruned path (FOP_CM_NO_PRUNE=1: A/B runs)
-  const bool try_prune = N > 8192 && model.time_change == FOP_TC_NONE && !no_skip &&
-                         !std::getenv("FOP_CM_NO_PRUNE");
   const size_t scratch_mark = h->arena_used;
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
     const int pc = (int)std::min<long long>(chunkP, P - p0);
@@ -693,6 +618,182 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
                                   cudaMemcpyDeviceToHost, h->stream));
   }
   if (out_host) FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return FOP_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// Caller-sampled entry points.  The reference takes ANY callable as characteristic function,
+// payoff and asset map (FSTSGeneric OptionPricing.h:155-163, CarrMadanGeneric :582-590); a device
+// kernel cannot call a host lambda, but it does not need to: the callable is only ever evaluated
+// on a grid the library defines, so the host samples it there (fop_fsts_u_grid /
+// fop_carr_madan_u_grid give the points) and everything after the evaluation -- option transform,
+// damping, Simpson weights, transforms, time stepping, early exercise, output map -- runs here.
+// ================================================================================================
+namespace {
+struct CmSampleGen {
+  static constexpr bool has_cf = false;
+  static size_t aux_bytes(int) { return 0; }
+  const cd* phi;  // [P][N]: cf(alpha + 1 + i j ada)
+  int N;
+  double ada, alpha, discount, b;
+  __device__ void prepare(void*, int, int) const {}
+  // same arithmetic as CmGen::operator() after the CF evaluation (OptionPricing.h:594-599)
+  __device__ cd operator()(const void*, int, int p, int j) const {
+    const double w = j * ada;
+    const cd den = mk(alpha * alpha + alpha - w * w, (2.0 * alpha + 1.0) * w);
+    const cd aug = cdiv(phi[(size_t)p * N + j], den);
+    const cd ph = cis(b * j * ada);
+    const double wt = j == 0 ? 1.0 : ((j & 1) ? 4.0 : 2.0);
+    const cd v = aug * ph;
+    const double sc = discount * wt;
+    return mk(v.x * sc, v.y * sc);
+  }
+};
+// m_k = enhCF(phi_k, i w_k) * scale from sampled phi (FFT order, getUDomain)
+__global__ void fsts_multiplier_samples_kernel(const cd* __restrict__ phi, int N, double dx, double r,
+                                               double scale, int greek, cd* __restrict__ mbuf) {
+  const int p = blockIdx.y;
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  if (k >= N) return;
+  const double vmax = M_PI / dx, du = 2.0 * vmax / N;
+  double wk = du * k;
+  if (wk > vmax) wk -= 2.0 * vmax;  // getUDomain, OptionPricing.h:19-23 (strict >)
+  const cd m = option_transform(greek, phi[(size_t)p * N + k], mk(0.0, wk), r);
+  mbuf[(size_t)p * N + k] = mk(m.x * scale, m.y * scale);
+}
+__global__ void fsts_payoff_samples_kernel(const double* __restrict__ pay, int per_set, int N, int P,
+                                           double* __restrict__ v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)P * N) return;
+  v[i] = pay[per_set ? i : i % N];
+}
+struct FstsRealSamplesEpi {
+  double* v;
+  const double* pay;    // [N] or [P][N]
+  const double* asset;  // [N] or nullptr
+  int N, per_set, american, kind_div;
+  __device__ void operator()(int p, int j, cd X) const {
+    double x = X.x;
+    if (american) x = fmax(x, pay[per_set ? (size_t)p * N + j : (size_t)j]);
+    if (kind_div) {
+      const double sj = asset[j];
+      x = kind_div == 1 ? x / sj : x / (sj * sj);
+    }
+    v[(size_t)p * N + j] = x;
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int fop_carr_madan_u_grid(int N, double ada, double alpha, double* u_out2) {
+  if (!u_out2 || N < 1) return FOP_INVALID_ARG;
+  for (int j = 0; j < N; ++j) {
+    u_out2[2 * j] = alpha + 1.0;
+    u_out2[2 * j + 1] = j * ada;
+  }
+  return FOP_OK;
+}
+
+int fop_carr_madan_cf_samples(fop_handle_t h, const double* cf_samples, int P, int N, double ada,
+                              double alpha, double S0, double r, double T, int is_put, double* out) {
+  if (!h) return FOP_INVALID_ARG;
+  if (!cf_samples || !out) return fail(h, FOP_INVALID_ARG, "null pointer");
+  if (P < 0 || N < 16 || (N & (N - 1)) || N > (1 << 20))
+    return fail(h, FOP_INVALID_ARG, "fop_carr_madan_cf_samples: N must be a power of two in [16, 2^20]");
+  if (P == 0) return FOP_OK;
+  FOP_CUDA(h, cudaSetDevice(h->device));
+  const bool out_host = !is_device_ptr(out);
+  Arena ar(h);
+  FOP_TRY(ar.reserve(stage_bytes(cf_samples, (size_t)P * N * 16) + (out_host ? Arena::pad((size_t)P * N * 8) : 0) +
+                     fft_scratch_bytes(N, P)));
+  const double* d_phi = nullptr;
+  FOP_TRY(stage_in(h, ar, cf_samples, (size_t)P * N * 2, &d_phi));
+  double* d_out = out_host ? ar.alloc<double>((size_t)P * N) : out;
+  const double b = M_PI / ada, lambda = 2.0 * b / N, discount = std::exp(-r * T);
+  CmSampleGen g{reinterpret_cast<const cd*>(d_phi), N, ada, alpha, discount, b};
+  CmEpi e{d_out, N, S0, alpha, b, lambda, ada, discount, is_put, nullptr};
+  FOP_TRY((run_fft<-1>(h, ar, N, P, g, e)));
+  if (out_host) {
+    FOP_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)P * N * 8, cudaMemcpyDeviceToHost, h->stream));
+    FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return FOP_OK;
+}
+
+int fop_fsts_u_grid(int N, double xmax, double* w_out) {
+  if (!w_out || N < 2) return FOP_INVALID_ARG;
+  const double dx = (2.0 * xmax) / ((double)N - 1.0), vmax = M_PI / dx, du = 2.0 * vmax / N;
+  for (int k = 0; k < N; ++k) {
+    double wk = du * k;
+    if (wk > vmax) wk -= 2.0 * vmax;
+    w_out[k] = wk;
+  }
+  return FOP_OK;
+}
+
+int fop_fsts_samples(fop_handle_t h, const double* cf_samples, const double* payoff, int payoff_per_set,
+                     const double* asset, int P, int N, double xmax, double r, double T, int steps,
+                     int american, int kind, double* out) {
+  if (!h) return FOP_INVALID_ARG;
+  if (!cf_samples || !payoff || !out) return fail(h, FOP_INVALID_ARG, "null pointer");
+  if (P < 0 || N < 16 || (N & (N - 1)) || N > (1 << 20) || steps < 1 || kind < 0 || kind > 3)
+    return fail(h, FOP_INVALID_ARG, "fop_fsts_samples: N power of two in [16, 2^20], steps >= 1");
+  if ((kind == FOP_FSTS_DELTA || kind == FOP_FSTS_GAMMA) && !asset)
+    return fail(h, FOP_INVALID_ARG, "fop_fsts_samples: delta / gamma need the asset grid");
+  if ((steps > 1 || american) && kind != FOP_FSTS_PRICE)
+    return fail(h, FOP_UNSUPPORTED, "fop_fsts_samples: time stepping / early exercise needs kind = price");
+  if (P == 0) return FOP_OK;
+  FOP_CUDA(h, cudaSetDevice(h->device));
+  const bool out_host = !is_device_ptr(out);
+  const size_t npay = payoff_per_set ? (size_t)P * N : (size_t)N;
+  const long long pcmax = std::max<long long>(1, std::min<long long>(P, (2ll << 30) / ((long long)N * 32)));
+  Arena ar(h);
+  FOP_TRY(ar.reserve(stage_bytes(cf_samples, (size_t)P * N * 16) + stage_bytes(payoff, npay * 8) +
+                     (asset ? stage_bytes(asset, (size_t)N * 8) : 0) +
+                     (out_host ? Arena::pad((size_t)P * N * 8) : 0) +
+                     2 * Arena::pad((size_t)pcmax * N * 16) + fft_scratch_bytes(N, (int)pcmax)));
+  const double *d_phi = nullptr, *d_pay = nullptr, *d_asset = nullptr;
+  FOP_TRY(stage_in(h, ar, cf_samples, (size_t)P * N * 2, &d_phi));
+  FOP_TRY(stage_in(h, ar, payoff, npay, &d_pay));
+  if (asset) FOP_TRY(stage_in(h, ar, asset, (size_t)N, &d_asset));
+  double* d_out = out_host ? ar.alloc<double>((size_t)P * N) : out;
+  cd* mbuf = ar.alloc<cd>((size_t)pcmax * N);
+  cd* ybuf = ar.alloc<cd>((size_t)pcmax * N);
+  if (!mbuf || !ybuf || !d_out) return fail(h, FOP_OOM, "arena exhausted (fop_fsts_samples)");
+  const double dx = (2.0 * xmax) / ((double)N - 1.0);
+  const double Tcf = T / steps, disc = std::exp(-r * Tcf);
+  const int greek = kind == 0 ? 0 : kind == 1 ? 1 : kind == 2 ? 2 : 3;
+  const size_t mark = h->arena_used;
+  for (long long p0 = 0; p0 < P; p0 += pcmax) {
+    const int pc = (int)std::min<long long>(pcmax, P - p0);
+    double* v = d_out + (size_t)p0 * N;
+    const double* pay0 = d_pay + (payoff_per_set ? (size_t)p0 * N : 0);
+    {
+      ProfScope ps(h, "fsts_multiplier_kernel");
+      fsts_multiplier_samples_kernel<<<dim3((N + 255) / 256, pc), 256, 0, h->stream>>>(
+          reinterpret_cast<const cd*>(d_phi) + (size_t)p0 * N, N, dx, r, disc / (double)N, greek, mbuf);
+    }
+    FOP_LAUNCH_CHECK(h);
+    fsts_payoff_samples_kernel<<<(unsigned)(((size_t)pc * N + 255) / 256), 256, 0, h->stream>>>(
+        pay0, payoff_per_set, N, pc, v);
+    FOP_LAUNCH_CHECK(h);
+    for (int st = 0; st < steps; ++st) {
+      const bool last = st == steps - 1;
+      h->arena_used = mark;
+      FOP_TRY((run_fft<-1>(h, ar, N, pc, FstsLoadReal{v, N}, FstsMulEpi{mbuf, ybuf, N})));
+      h->arena_used = mark;
+      FOP_TRY((run_fft<1>(h, ar, N, pc, LoadGen{ybuf, N},
+                          FstsRealSamplesEpi{v, pay0, d_asset, N, payoff_per_set, american ? 1 : 0,
+                                             last && (kind == 1 || kind == 2) ? kind : 0})));
+    }
+  }
+  if (out_host) {
+    FOP_CUDA(h, cudaMemcpyAsync(out, d_out, (size_t)P * N * 8, cudaMemcpyDeviceToHost, h->stream));
+    FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   return FOP_OK;
 }
 

@@ -30,84 +30,118 @@ struct CosCoeffArgs {
 constexpr int COEFF_MAX_SPB = 64;
 
 // Running power of E = exp(-delta dt) along the maturity list (maturities on the grid T_m = n_m dt,
-// a.npow != nullptr): exp(-delta T_m) = E^{n_m} = R_{m-1} * E^{d_m}.  The host encodes d_m =
-// n_m - n_{m-1} (> 0 for an ascending list, the usual case; < 0 means "restart: E^{-d_m} from 1").
-// E^{d} comes from binary powering and is kept while consecutive steps repeat (monthly lists: 1, 2,
-// 3, 3, 3, 6, 6, 12 -> five powerings, 12 loop trips per (set, u) pair).  All branches are uniform
-// over the grid.  This replaces one exp + sincos per maturity -- a quarter of the fp64 work of a
-// Heston coefficient -- by one complex multiplication.
+// ascending; a.npow != nullptr): exp(-delta T_m) = E^{n_m} = R_{m-1} * E^{d_m} with the steps d_m =
+// n_m - n_{m-1} >= 0 supplied by the host (cos_host_tables.h; a list that is not ascending does not
+// use the grid).  E^{d} is kept while consecutive steps repeat, squared when the step doubles, and
+// otherwise formed by binary powering (monthly lists: d = 1, 2, 3, 3, 3, 6, 6, 12 -> E, a square,
+// one powering, two squares per (set, u) pair).  All branches are uniform over the grid.  This
+// replaces one exp + sincos per maturity -- a quarter of the fp64 work of a Heston coefficient --
+// by one complex multiplication.
 struct PowState {
   cd R, D;     // R = E^{n_{m-1}}, D = E^{dprev}
   int dprev;
 };
+__host__ __device__ __forceinline__ cd csquare(cd z) { return mk(z.x * z.x - z.y * z.y, 2.0 * z.x * z.y); }
 __host__ __device__ __forceinline__ cd pow_step(PowState& ps, cd E, int d) {
-  if (d < 0) {
-    ps.R = mk(1.0, 0.0);
-    d = -d;
-  }
   if (d != ps.dprev) {
-    cd acc = mk(1.0, 0.0), S = E;
-    for (int b = d; b != 0; b >>= 1) {
-      if (b & 1) acc = acc * S;
-      S = mk(S.x * S.x - S.y * S.y, 2.0 * S.x * S.y);
+    if (d == 2 * ps.dprev) {
+      ps.D = csquare(ps.D);
+    } else if (d == 1) {
+      ps.D = E;
+    } else {
+      cd acc = mk(1.0, 0.0), S = E;
+      for (int b = d; b != 0; b >>= 1) {
+        if (b & 1) acc = acc * S;
+        S = csquare(S);
+      }
+      ps.D = acc;
     }
-    ps.D = acc;
     ps.dprev = d;
   }
   ps.R = ps.R * ps.D;
   return ps.R;
 }
 
-// N maturities m .. m + N - 1 of one (set, u) pair, advanced operation by operation (VD<N>).
-template <int MODE, int N>
+// GRID: the maturities sit on a common grid (a.npow != nullptr; decided once per launch, outside the
+// loops).  GMASK >= 0: the set of emitted transforms is a compile-time constant (1 = price only).
+// FAST: CIR clock through the re-associated form (cir_logphi_fast) -- specialised kernels; the
+// generic kernel keeps the term-by-term form of the reference (cf_log_cir_given_e).
+template <int MODE, int N, bool GRID, int GMASK = -1, bool FAST = false>
 __host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, const ModelConsts& mc,
-                                            const CfPre& pre, cd E, PowState& ps, cd u, double v,
-                                            double2* crow, int Kp, int m) {
+                                            const CfPre& pre, const CirFast& cf, cd E, PowState& ps,
+                                            cd u, double v, double2* crow, int Kp, int m) {
+  // crow points at maturity m of this (set, u) pair (the caller advances it: no 64-bit row
+  // multiplication per store)
   VD<N> Tm;
 #pragma unroll
   for (int i = 0; i < N; ++i) Tm.v[i] = FOP_LDG(a.T + m + i);
   cx<VD<N>> lphi;
-  if (MODE == CF_MODE_CIR && a.npow) {
+  if (MODE == CF_MODE_CIR && (GRID || FAST)) {
     cx<VD<N>> e;
+    if (GRID) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const cd r = pow_step(ps, E, FOP_LDG(a.npow + m + i));
-      e.x.v[i] = r.x;
-      e.y.v[i] = r.y;
+      for (int i = 0; i < N; ++i) {
+        const cd r = pow_step(ps, E, FOP_LDG(a.npow + m + i));
+        e.x.v[i] = r.x;
+        e.y.v[i] = r.y;
+      }
+    } else {
+      e = cexp(mk(-pre.delta.x * Tm, -pre.delta.y * Tm));
     }
-    const cx<VD<N>> l = mk(pre.lin.x * Tm, pre.lin.y * Tm);
-    lphi = cf_log_cir_given_e(mc, pre, Tm, l, e);
+    if (FAST) {
+      lphi = cir_logphi_fast(cf, Tm, e);
+    } else {
+      const cx<VD<N>> l = mk(pre.lin.x * Tm, pre.lin.y * Tm);
+      lphi = cf_log_cir_given_e(mc, pre, Tm, l, e);
+    }
   } else {
     lphi = cf_log_at_mode<MODE>(mc, pre, Tm);
+  }
+  const int gmask = GMASK >= 0 ? GMASK : a.greek_mask;
+  if (gmask == 1) {  // price only: V_k cp folded into the exponential's scale
+    const cx<VD<N>> t = cexp_scaled(lphi, v);
+#pragma unroll
+    for (int i = 0; i < N; ++i) crow[(size_t)i * Kp] = make_double2(t.x.v[i], t.y.v[i]);
+    return;
   }
   const cx<VD<N>> d = cexp(lphi);
   // one CF evaluation feeds every requested transform (price / delta / gamma / theta)
   double2* cg = crow;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    if (!(a.greek_mask >> g & 1)) continue;
+    if (!(gmask >> g & 1)) continue;
     const cx<VD<N>> t = option_transform(g, d, u, a.r);
 #pragma unroll
-    for (int i = 0; i < N; ++i) cg[(size_t)(m + i) * Kp] = make_double2(t.x.v[i] * v, t.y.v[i] * v);
+    for (int i = 0; i < N; ++i) cg[(size_t)i * Kp] = make_double2(t.x.v[i] * v, t.y.v[i] * v);
     cg += a.plane / 2;
   }
 }
 
 // all maturities of one (set, u) pair, ILP at a time
-template <int MODE, int ILP>
-__host__ __device__ __forceinline__ void coeff_maturities(const CosCoeffArgs& a, const ModelConsts& mc,
+template <int MODE, int ILP, bool GRID, int GMASK = -1, bool FAST = false>
+__host__ __device__ __forceinline__ void coeff_maturities_g(const CosCoeffArgs& a, const ModelConsts& mc,
                                                  const CfPre& pre, cd u, double v, double2* crow,
                                                  int Kp) {
   cd E = mk(1.0, 0.0);
-  if (MODE == CF_MODE_CIR && a.npow) E = cexp(mk(-pre.delta.x * a.dt, -pre.delta.y * a.dt));
+  if (MODE == CF_MODE_CIR && GRID) E = cexp(mk(-pre.delta.x * a.dt, -pre.delta.y * a.dt));
+  CirFast cf;
+  if (MODE == CF_MODE_CIR && FAST) cf = cir_fast_prepare(mc, pre);
   PowState ps;
   ps.R = mk(1.0, 0.0);
   ps.D = mk(1.0, 0.0);
   ps.dprev = 0;
   const int M = a.M;
   int m = 0;
-  for (; m + ILP <= M; m += ILP) coeff_group<MODE, ILP>(a, mc, pre, E, ps, u, v, crow, Kp, m);
-  for (; m < M; ++m) coeff_group<MODE, 1>(a, mc, pre, E, ps, u, v, crow, Kp, m);
+  for (; m + ILP <= M; m += ILP, crow += (size_t)ILP * Kp)
+    coeff_group<MODE, ILP, GRID, GMASK, FAST>(a, mc, pre, cf, E, ps, u, v, crow, Kp, m);
+  for (; m < M; ++m, crow += Kp) coeff_group<MODE, 1, GRID, GMASK, FAST>(a, mc, pre, cf, E, ps, u, v, crow, Kp, m);
+}
+template <int MODE, int ILP, int GMASK = -1>
+__host__ __device__ __forceinline__ void coeff_maturities(const CosCoeffArgs& a, const ModelConsts& mc,
+                                                 const CfPre& pre, cd u, double v, double2* crow,
+                                                 int Kp) {
+  if (MODE == CF_MODE_CIR && a.npow) coeff_maturities_g<MODE, ILP, true, GMASK>(a, mc, pre, u, v, crow, Kp);
+  else coeff_maturities_g<MODE, ILP, false, GMASK>(a, mc, pre, u, v, crow, Kp);
 }
 
 // Output map of the reference entry points (OptionPricing.h:378,414,439,464,490,515,541) as

@@ -40,12 +40,15 @@ inline bool maturity_grid(const std::vector<double>& T, double* dt_out, std::vec
   return false;
 }
 
-// steps along the maturity list for pow_step (cos_coeff.cuh): d_m = n_m - n_{m-1} (n_{-1} = 0); a
-// descending step restarts from 1 (encoded as -n_m)
+// steps along the maturity list for pow_step (cos_coeff.cuh): d_m = n_m - n_{m-1} (n_{-1} = 0);
+// empty when the list is not ascending (the grid shortcut is then not used)
 inline std::vector<int> maturity_steps(const std::vector<int>& n) {
   std::vector<int> steps(n.size());
-  for (size_t m = 0, prev = 0; m < n.size(); prev = n[m], ++m)
-    steps[m] = n[m] >= (int)prev ? n[m] - (int)prev : -n[m];
+  int prev = 0;
+  for (size_t m = 0; m < n.size(); prev = n[m], ++m) {
+    if (n[m] < prev) return {};
+    steps[m] = n[m] - prev;
+  }
   return steps;
 }
 

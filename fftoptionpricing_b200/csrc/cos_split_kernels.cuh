@@ -20,17 +20,20 @@
 
 namespace fop {
 
-template <int ILP, int NT = 256, int MINB = 2>
+// BASE / TC < 0: taken from the arguments at run time (generic kernel); >= 0: compile-time model
+// (specialised kernels, capi_cos_coeff.cu)
+template <int ILP, int NT = 256, int MINB = 2, int BASE = -1, int TC = -1>
 __global__ void __launch_bounds__(NT, MINB) cos_coeff_kernel(const CosCoeffArgs a) {
   __shared__ ModelConsts consts[COEFF_MAX_SPB];
   const int tid = threadIdx.x;
   const int K = a.K, M = a.M;
+  const int base = BASE >= 0 ? BASE : a.base, tc = TC >= 0 ? TC : a.tc;
   const int ngroups = (a.P + a.spb - 1) / a.spb;
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int p0 = grp * a.spb;
     const int nsets = min(a.spb, a.P - p0);
     __syncthreads();
-    if (tid < nsets) make_consts(a.base, a.tc, a.params + (size_t)(p0 + tid) * a.np, consts[tid]);
+    if (tid < nsets) make_consts(base, tc, a.params + (size_t)(p0 + tid) * a.np, consts[tid]);
     __syncthreads();
     const int Kp = a.Kp;
     for (int idx = tid; idx < nsets * Kp; idx += NT) {
@@ -49,12 +52,53 @@ __global__ void __launch_bounds__(NT, MINB) cos_coeff_kernel(const CosCoeffArgs 
       const cd u = mk(0.0, __ldg(a.uk + k));
       const double v = __ldg(a.vk + k);
       CfPre pre;
-      cf_prepare(a.base, a.tc, mc, u, a.r, pre);
-      const int mode = cf_mode(a.tc, mc);
+      cf_prepare(base, tc, mc, u, a.r, pre);
+      const int mode = cf_mode(tc, mc);
       if (mode == CF_MODE_CIR) coeff_maturities<CF_MODE_CIR, ILP>(a, mc, pre, u, v, crow, Kp);
       else if (mode == CF_MODE_LEVY) coeff_maturities<CF_MODE_LEVY, ILP>(a, mc, pre, u, v, crow, Kp);
       else coeff_maturities<CF_MODE_DET, 1>(a, mc, pre, u, v, crow, Kp);
     }
+  }
+}
+
+// Coefficients from caller-sampled characteristic-function values (fop_cos_cf_samples: the
+// reference's arbitrary CF callable, FangOostGeneric OptionPricing.h:325-333, evaluated by the host
+// at i u_k): option transform, times V_k cp, zero padding -- then the same contraction.
+struct CosSampleArgs {
+  int greek_mask;
+  size_t plane;
+  long long rows;      // sets * maturities of this chunk
+  int K, Kp;
+  double r;
+  const double* phi;   // [rows][K][2]
+  const double* uk;
+  const double* vk;
+  double* C;
+};
+static __global__ void cos_coeff_samples_kernel(const CosSampleArgs a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.rows * a.Kp) return;
+  const long long row = idx / a.Kp;
+  const int k = (int)(idx - row * a.Kp);
+  double2* cg = reinterpret_cast<double2*>(a.C) + row * a.Kp + k;
+  const bool pad = k >= a.K;
+  cd phi = mk(0.0, 0.0), u = mk(0.0, 0.0);
+  double v = 0.0;
+  if (!pad) {
+    const double2 f = reinterpret_cast<const double2*>(a.phi)[row * a.K + k];
+    phi = mk(f.x, f.y);
+    u = mk(0.0, a.uk[k]);
+    v = a.vk[k];
+  }
+  for (int g = 0; g < 4; ++g) {
+    if (!(a.greek_mask >> g & 1)) continue;
+    if (pad) {
+      *cg = make_double2(0.0, 0.0);
+    } else {
+      const cd t = option_transform(g, phi, u, a.r);
+      *cg = make_double2(t.x * v, t.y * v);
+    }
+    cg += a.plane / 2;
   }
 }
 

@@ -47,6 +47,13 @@ template <class T> CX_HD cx<T> cexp(cx<T> z) {
   fm_sincos(z.y, &s, &c);
   return mk(e * c, e * s);
 }
+// v e^z (one multiplication fewer than v * cexp(z))
+template <class T> CX_HD cx<T> cexp_scaled(cx<T> z, double v) {
+  const T e = fm_exp(z.x) * v;
+  T s, c;
+  fm_sincos(z.y, &s, &c);
+  return mk(e * c, e * s);
+}
 // e^{i t}
 CX_HD cd cis(double t) {
   double s, c;

@@ -156,7 +156,12 @@ FM_HD double fm_rcp_seed(double b) {  // >= 20 correct bits; b normal, nonzero
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
   return r;
 #else
-  return 1.0 / b;  // host build is a test harness only
+  // host build (test harness): mimic MUFU.RCP64H -- only the high word of the operand is read and
+  // only the high word of the result is produced (~20 correct bits), so that the Newton steps are
+  // exercised with a seed as coarse as the device's
+  long long bits; memcpy(&bits, &b, 8); bits &= 0xffffffff00000000ll; double bh; memcpy(&bh, &bits, 8);
+  double r = 1.0 / bh; memcpy(&bits, &r, 8); bits &= 0xffffffff00000000ll; memcpy(&r, &bits, 8);
+  return r;
 #endif
 }
 FM_HD double fm_sqrt(double x) { return sqrt(x); }
@@ -190,9 +195,11 @@ template <class T> FM_HD T fm_rcp(T b) {
   r = fm_fma(r, e, r);
   return r;
 }
-// a / b to <= 1 ulp for normal-range operands
+// a / b to <= 1 ulp for normal-range operands.  One Newton step suffices for the reciprocal (seed
+// 2^-20 -> 2^-40): the residual correction of the quotient squares that error again (2^-80).
 template <class T> FM_HD T fm_div(T a, T b) {
-  const T r = fm_rcp(b);
+  T r = fm_rcp_seed(b);
+  r = fm_fma(r, fm_fma(-b, r, 1.0), r);
   const T q = a * r;
   return fm_fma(fm_fma(-b, q, a), r, q);
 }
@@ -287,23 +294,31 @@ template <bool SCALE, class T> FM_HD T fm_atan2_impl(T y, T x) {
     ax = ax * sc;
     ay = ay * sc;
   }
-  const auto xbig = ax > ay;
-  const T mx = fm_sel(xbig, ax, ay), mn = fm_sel(xbig, ay, ax);
+  const auto ybig = ay > ax;
+  const T mx = fm_sel(ybig, ay, ax), mn = fm_sel(ybig, ax, ay);
   const auto big = mn > K[9] * mx;  // tan(pi/8)
   const T num = fm_sel(big, mn - mx, mn);
   T den = fm_sel(big, mn + mx, mx);
-  den = fm_sel(den == 0.0, 1.0, den);  // atan2(0, 0): t = 0
+  if (SCALE) den = fm_sel(den == 0.0, 1.0, den);  // atan2(0, 0): t = 0
   const T t = fm_div(num, den);
   const T z = t * t;
   FM_TABPTR A = FM_TAB(fm_atan_t);
   T p = fm_fma(z, A[0], A[1]);
 #pragma unroll
   for (int i = 2; i < 11; ++i) p = fm_fma(p, z, A[i]);
-  T a = fm_fma(-t, z * p, t);
-  // + pi/4 (hi + lo) when reduced
-  a = fm_sel(big, K[10] + (a + K[11]), a);
-  a = fm_sel(ay > ax, K[12] - (a - K[13]), a);
-  a = fm_sel(fm_hi(x) < 0, K[14] - (a - K[15]), a);
+  const T a0 = fm_fma(-t, z * p, t);  // atan(t), |t| <= tan(pi/8)
+  // The octant fix-ups  a1 = pi/4 + a0 (big);  a2 = pi/2 - a1 (|y| > |x|);  a3 = pi - a2 (x < 0)
+  // collapse to  m (pi/4) + s a0  with an integer m in 0..4 and a sign s: integer selects and one
+  // fused multiply-add pair replace three select / subtract ladders on doubles.
+  const auto neg = fm_hi(x) < 0;
+  auto m = fm_sel(big, 1, 0);
+  m = fm_sel(ybig, 2 - m, m);
+  m = fm_sel(neg, 4 - m, m);
+  // s = -1 iff exactly one of (|y| > |x|), (x < 0)
+  const auto sflip = fm_sel(ybig, (int)0x80000000, 0) ^ (fm_hi(x) & (int)0x80000000);
+  const T a0s = fm_make(fm_hi(a0) ^ sflip, fm_lo(a0));
+  const T md = fm_i2d(m);
+  const T a = fm_fma(md, K[10], fm_fma(md, K[11], a0s));  // m pi/4 (hi + lo) + s a0
   return fm_make(fm_hi(a) ^ (fm_hi(y) & 0x80000000), fm_lo(a));
 }
 template <class T> FM_HD T fm_atan2(T y, T x) { return fm_atan2_impl<true>(y, x); }

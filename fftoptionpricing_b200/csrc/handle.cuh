@@ -35,6 +35,10 @@ struct fop_handle_s {
   // optional NCCL communicator (capi_comm.cu; opaque here, NCCL is bound at run time)
   void* comm = nullptr;
   int comm_rank = 0, comm_world = 0;
+  // side stream of fop_gather_losses_async (the gather overlaps the next step's kernels)
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_ready = nullptr, comm_done = nullptr;
+  bool comm_pending = false;
   // optional per-kernel device timing (fop_profile_*): accumulated by kernel name
   bool profiling = false;
   struct ProfEntry { std::string name; double ms = 0; long long launches = 0; };

@@ -55,11 +55,17 @@ class _Buf:
             self.is_device = x.is_cuda
             self.size = x.numel()
             return
-        a = np.asarray(x, dtype=dtype)
         if writable:
-            assert a.flags.c_contiguous and a.flags.writeable
+            # an output buffer is never converted: a silent copy would be filled instead of the
+            # caller's array
+            if not isinstance(x, np.ndarray) or x.dtype != np.dtype(dtype):
+                raise TypeError(f"output buffer must be a numpy array of dtype {np.dtype(dtype)}, got "
+                                f"{type(x).__name__} {getattr(x, 'dtype', '')}")
+            if not (x.flags.c_contiguous and x.flags.writeable):
+                raise TypeError("output buffer must be C-contiguous and writeable")
+            a = x
         else:
-            a = np.ascontiguousarray(a)
+            a = np.ascontiguousarray(np.asarray(x, dtype=dtype))
         if shape is not None:
             a = a.reshape(shape)
         self.keep = a
@@ -233,6 +239,17 @@ class Engine:
         self._check(self._L.fop_gather_losses(self._h, b.ptr, b.size, ob.ptr))
         return o
 
+    def gather_losses_async(self, loss_local, out):
+        """Side-stream all-gather of device-resident losses (torch CUDA tensors), overlapped with
+        whatever is enqueued next; ``comm_wait`` orders the handle's stream after it."""
+        b, ob = _Buf(loss_local), _Buf(out)
+        assert b.is_device and ob.is_device and ob.size == self._world * b.size
+        self._check(self._L.fop_gather_losses_async(self._h, b.ptr, b.size, ob.ptr))
+        return out
+
+    def comm_wait(self):
+        self._check(self._L.fop_comm_wait(self._h))
+
     def calibrate_cf(self, base, tc, lower, upper, u, phiHat, r, T, nests=25, iterations=1500,
                      tol=1e-12, seed=42, restarts=1):
         """On-device cuckoo search over the objective of ``objfn_cf`` (replaces the reference's
@@ -306,6 +323,72 @@ class Engine:
                                               float(outputMin), float(inputMin), float(inputMax),
                                               int(bool(inverse)), C.c_void_p(o.ctypes.data)))
         return o
+
+    # ------------------------------------------------------------------ caller-sampled CF / payoff
+    def cos_u_grid(self, K_desc, S0, numU):
+        """u_k at which fop_cos_cf_samples expects cf(1j * u_k)."""
+        K = np.ascontiguousarray(np.asarray(K_desc, dtype=np.float64))
+        out = np.empty(int(numU))
+        st = self._L.fop_cos_u_grid(K.ctypes.data_as(_lib._dp), K.size, float(S0), int(numU),
+                                    out.ctypes.data_as(_lib._dp))
+        if st != 0:
+            raise FopError(st, "fop_cos_u_grid: bad arguments")
+        return out
+
+    def cos_cf_samples(self, cf_samples, K_desc, S0, r, T, numU, kind=0, out=None):
+        """COS prices from sampled characteristic-function values cf_samples[P][M][numU] (complex):
+        the reference's arbitrary-callable signature (FangOostGeneric, OptionPricing.h:325-333)."""
+        Kb = _Buf(K_desc)
+        Tb = _Buf(np.atleast_1d(np.asarray(T, dtype=np.float64)))
+        if _is_torch(cf_samples):
+            sb = _Buf(cf_samples, dtype=np.complex128)
+            n = cf_samples.numel()
+        else:
+            z = np.ascontiguousarray(np.asarray(cf_samples, dtype=np.complex128))
+            sb = _Buf(z.view(np.float64))
+            n = z.size
+        P = n // (Tb.size * int(numU))
+        assert P * Tb.size * int(numU) == n, "cf_samples must be [P][M][numU]"
+        out, ob = self._out(out, (P, Tb.size, Kb.size))
+        self._check(self._L.fop_cos_cf_samples(self._h, sb.ptr, P, Kb.ptr, Kb.size, float(S0), float(r),
+                                               Tb.ptr, Tb.size, int(numU), int(kind), ob.ptr))
+        return out
+
+    def carr_madan_u_grid(self, N, ada, alpha=1.5):
+        out = np.empty(2 * int(N))
+        self._L.fop_carr_madan_u_grid(int(N), float(ada), float(alpha), out.ctypes.data_as(_lib._dp))
+        return out.view(np.complex128)
+
+    def carr_madan_cf_samples(self, cf_samples, N, ada, alpha, S0, r, T, is_put=False, out=None):
+        """cf_samples[P][N] (complex) = cf(alpha + 1 + 1j * j * ada): CarrMadanGeneric with an
+        arbitrary callable (OptionPricing.h:582-607)."""
+        z = np.ascontiguousarray(np.asarray(cf_samples, dtype=np.complex128)).reshape(-1, int(N))
+        out, ob = self._out(out, (z.shape[0], int(N)))
+        self._check(self._L.fop_carr_madan_cf_samples(self._h, C.c_void_p(z.ctypes.data), z.shape[0], int(N),
+                                                      float(ada), float(alpha), float(S0), float(r), float(T),
+                                                      int(bool(is_put)), ob.ptr))
+        return out
+
+    def fsts_u_grid(self, N, xmax):
+        out = np.empty(int(N))
+        self._L.fop_fsts_u_grid(int(N), float(xmax), out.ctypes.data_as(_lib._dp))
+        return out
+
+    def fsts_samples(self, cf_samples, payoff, N, xmax, r, T, steps=1, american=False, kind=0, asset=None,
+                     out=None):
+        """FSTSGeneric with arbitrary callables (OptionPricing.h:155-184): cf_samples[P][N] (complex) =
+        cf(1j * w_k) for the step length T/steps, payoff[N] or [P][N], asset[N] for delta / gamma."""
+        z = np.ascontiguousarray(np.asarray(cf_samples, dtype=np.complex128)).reshape(-1, int(N))
+        P = z.shape[0]
+        pay = np.ascontiguousarray(np.asarray(payoff, dtype=np.float64))
+        per_set = 1 if pay.size == P * int(N) and P > 1 else 0
+        assert pay.size in (int(N), P * int(N))
+        ab = _Buf(asset)
+        out, ob = self._out(out, (P, int(N)))
+        self._check(self._L.fop_fsts_samples(self._h, C.c_void_p(z.ctypes.data), C.c_void_p(pay.ctypes.data), per_set,
+                                             ab.ptr, P, int(N), float(xmax), float(r), float(T), int(steps),
+                                             int(bool(american)), int(kind), ob.ptr))
+        return out
 
     # ------------------------------------------------------------------ grids (host)
     def carr_madan_strikes(self, N, ada, S0):

@@ -2,10 +2,12 @@
 // (namespace optionprice, reference OptionPricing.h) over the C ABI of fftop_b200.h.
 //
 // Differences from the reference, by necessity of running on a GPU:
-//  * the characteristic function argument is a model descriptor fftop::CF (closed set: exactly the
-//    CFs of test.cpp / generateCharts.cpp) instead of an arbitrary callable;
-//  * FSTS takes the strike and a payoff kind instead of getAssetPrice / payoff lambdas (the
-//    reference's tests always use asset = K e^x and call/put payoffs, test.cpp:56-61,202-204).
+//  * the fast path takes the characteristic function as a model descriptor fftop::CF (closed set:
+//    exactly the CFs of test.cpp / generateCharts.cpp), evaluated on the device;
+//  * the reference's own signatures -- ANY callable as characteristic function, payoff and asset map
+//    (FangOostGeneric OptionPricing.h:325-333, CarrMadanGeneric :582-590, FSTSGeneric :155-163) --
+//    are kept as overloads: the callable is evaluated by the host on the grid the library defines
+//    and the samples go through fop_*_samples, everything else runs on the GPU.
 // Everything else -- names, argument order and meaning, return by value as std::vector<double>
 // (or the caller's strike container for COS, test.cpp:574 uses std::deque) -- is the reference's.
 // Like the reference, no argument validation is reported to the caller except through
@@ -13,9 +15,11 @@
 #ifndef FFTOP_OPTIONPRICING_H
 #define FFTOP_OPTIONPRICING_H
 #include <cmath>
+#include <complex>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../fftop_b200.h"
@@ -105,6 +109,20 @@ inline std::vector<double> getCarrMadanStrikes(double ada, double S0, int numX) 
   return v;
 }
 
+// getFangOostKAtIndex (OptionPricing.h:93-97), getXFromK (:110-117), getCarrMadanKAtIndex (:121-123)
+inline double getFangOostKAtIndex(double xMin, double dK, double S0, int index) {
+  return S0 * std::exp(-(xMin + dK * index));
+}
+template <typename Array>
+Array getXFromK(double S0, const Array& K) {
+  std::vector<double> x;
+  for (const auto& k : K) x.push_back(std::log(S0 / k));
+  return Array(x.begin(), x.end());
+}
+inline double getCarrMadanKAtIndex(double b, double lambda, double S0, int index) {
+  return S0 * std::exp(-b + lambda * index);
+}
+
 // ---- Carr-Madan (OptionPricing.h:620-704)
 inline std::vector<double> CarrMadanCall(int numSteps, double ada, double alpha, double S0, double r,
                                          double T, const fftop::CF& cf) {
@@ -186,6 +204,110 @@ inline std::vector<double> FSTSGamma(int numSteps, double xmax, double r, double
 inline std::vector<double> FSTSTheta(int numSteps, double xmax, double r, double T, double strike,
                                      fftop::Payoff payoff, const fftop::CF& cf) {
   return detail::fsts(FOP_FSTS_THETA, numSteps, xmax, r, T, strike, payoff, cf);
+}
+
+// ---- the reference's own signatures with an arbitrary callable characteristic function ---------
+// `cf` is any callable std::complex<double> -> std::complex<double> (what the reference's templates
+// take); it is sampled here, on the host, at the points the pricer needs.
+namespace detail {
+template <typename F> struct is_descriptor : std::is_same<typename std::decay<F>::type, fftop::CF> {};
+template <typename F> using callable_t = typename std::enable_if<!is_descriptor<F>::value, int>::type;
+
+template <typename CFn>
+std::vector<double> carrMadanSampled(int numSteps, double ada, double alpha, double S0, double r, double T,
+                                     CFn&& cf, int isPut) {
+  auto& e = fftop::Engine::instance();
+  std::vector<double> u(2 * (size_t)numSteps), phi(2 * (size_t)numSteps), out(numSteps);
+  fop_carr_madan_u_grid(numSteps, ada, alpha, u.data());
+  for (int j = 0; j < numSteps; ++j) {
+    const std::complex<double> v = cf(std::complex<double>(u[2 * j], u[2 * j + 1]));
+    phi[2 * j] = v.real();
+    phi[2 * j + 1] = v.imag();
+  }
+  e.check(fop_carr_madan_cf_samples(e.get(), phi.data(), 1, numSteps, ada, alpha, S0, r, T, isPut, out.data()));
+  return out;
+}
+template <typename Array, typename CFn>
+Array cosSampled(int kind, double S0, const Array& K, double r, double T, int numU, CFn&& cf) {
+  auto& e = fftop::Engine::instance();
+  std::vector<double> k(K.begin(), K.end()), out(k.size()), u(numU), phi(2 * (size_t)numU);
+  fop_cos_u_grid(k.data(), (int)k.size(), S0, numU, u.data());
+  for (int i = 0; i < numU; ++i) {
+    const std::complex<double> v = cf(std::complex<double>(0.0, u[i]));
+    phi[2 * i] = v.real();
+    phi[2 * i + 1] = v.imag();
+  }
+  e.check(fop_cos_cf_samples(e.get(), phi.data(), 1, k.data(), (int)k.size(), S0, r, &T, 1, numU, kind, out.data()));
+  return Array(out.begin(), out.end());
+}
+template <typename GetAssetPrice, typename PayoffFn, typename CFn>
+std::vector<double> fstsSampled(int kind, int numSteps, double xmax, double r, double T, GetAssetPrice&& getAssetPrice,
+                                PayoffFn&& payoff, CFn&& cf, int steps = 1, bool american = false) {
+  auto& e = fftop::Engine::instance();
+  const double dx = 2.0 * xmax / (numSteps - 1.0);  // fangoost::computeDX(numSteps, -xmax, xmax)
+  std::vector<double> w(numSteps), phi(2 * (size_t)numSteps), pay(numSteps), asset(numSteps), out(numSteps);
+  fop_fsts_u_grid(numSteps, xmax, w.data());
+  for (int j = 0; j < numSteps; ++j) {
+    asset[j] = getAssetPrice(-xmax + dx * j);
+    pay[j] = payoff(asset[j]);
+    const std::complex<double> v = cf(std::complex<double>(0.0, w[j]));
+    phi[2 * j] = v.real();
+    phi[2 * j + 1] = v.imag();
+  }
+  e.check(fop_fsts_samples(e.get(), phi.data(), pay.data(), 0, asset.data(), 1, numSteps, xmax, r, T, steps,
+                           american ? 1 : 0, kind, out.data()));
+  return out;
+}
+}  // namespace detail
+
+template <typename CFn, detail::callable_t<CFn> = 0>
+std::vector<double> CarrMadanCall(int numSteps, double ada, double alpha, double S0, double r, double T, CFn&& cf) {
+  return detail::carrMadanSampled(numSteps, ada, alpha, S0, r, T, cf, 0);
+}
+template <typename CFn, detail::callable_t<CFn> = 0>
+std::vector<double> CarrMadanPut(int numSteps, double ada, double alpha, double S0, double r, double T, CFn&& cf) {
+  return detail::carrMadanSampled(numSteps, ada, alpha, S0, r, T, cf, 1);
+}
+template <typename CFn, detail::callable_t<CFn> = 0>
+std::vector<double> CarrMadanCall(int numSteps, double ada, double S0, double r, double T, CFn&& cf) {
+  return detail::carrMadanSampled(numSteps, ada, 1.5, S0, r, T, cf, 0);
+}
+template <typename CFn, detail::callable_t<CFn> = 0>
+std::vector<double> CarrMadanPut(int numSteps, double ada, double S0, double r, double T, CFn&& cf) {
+  return detail::carrMadanSampled(numSteps, ada, 1.5, S0, r, T, cf, 1);
+}
+#define FFTOP_COS_CALLABLE(NAME, KIND)                                                       \
+  template <typename Array, typename CFn, detail::callable_t<CFn> = 0>                       \
+  Array NAME(double S0, const Array& K, double r, double T, int numUSteps, CFn&& cf) {        \
+    return detail::cosSampled(KIND, S0, K, r, T, numUSteps, cf);                             \
+  }
+FFTOP_COS_CALLABLE(FangOostCallPrice, FOP_CALL_PRICE)
+FFTOP_COS_CALLABLE(FangOostPutPrice, FOP_PUT_PRICE)
+FFTOP_COS_CALLABLE(FangOostCallDelta, FOP_CALL_DELTA)
+FFTOP_COS_CALLABLE(FangOostPutDelta, FOP_PUT_DELTA)
+FFTOP_COS_CALLABLE(FangOostCallGamma, FOP_CALL_GAMMA)
+FFTOP_COS_CALLABLE(FangOostPutGamma, FOP_PUT_GAMMA)
+FFTOP_COS_CALLABLE(FangOostCallTheta, FOP_CALL_THETA)
+FFTOP_COS_CALLABLE(FangOostPutTheta, FOP_PUT_THETA)
+#undef FFTOP_COS_CALLABLE
+// FSTSPrice(numSteps, xmax, r, T, getAssetPrice, payoff, cf) etc. -- the reference's argument list
+// (OptionPricing.h:185-281); steps / american extend it (README.md:19)
+template <typename G, typename Pf, typename CFn, detail::callable_t<CFn> = 0>
+std::vector<double> FSTSPrice(int numSteps, double xmax, double r, double T, G&& getAssetPrice, Pf&& payoff, CFn&& cf,
+                              int steps = 1, bool american = false) {
+  return detail::fstsSampled(FOP_FSTS_PRICE, numSteps, xmax, r, T, getAssetPrice, payoff, cf, steps, american);
+}
+template <typename G, typename Pf, typename CFn, detail::callable_t<CFn> = 0>
+std::vector<double> FSTSDelta(int numSteps, double xmax, double r, double T, G&& getAssetPrice, Pf&& payoff, CFn&& cf) {
+  return detail::fstsSampled(FOP_FSTS_DELTA, numSteps, xmax, r, T, getAssetPrice, payoff, cf);
+}
+template <typename G, typename Pf, typename CFn, detail::callable_t<CFn> = 0>
+std::vector<double> FSTSGamma(int numSteps, double xmax, double r, double T, G&& getAssetPrice, Pf&& payoff, CFn&& cf) {
+  return detail::fstsSampled(FOP_FSTS_GAMMA, numSteps, xmax, r, T, getAssetPrice, payoff, cf);
+}
+template <typename G, typename Pf, typename CFn, detail::callable_t<CFn> = 0>
+std::vector<double> FSTSTheta(int numSteps, double xmax, double r, double T, G&& getAssetPrice, Pf&& payoff, CFn&& cf) {
+  return detail::fstsSampled(FOP_FSTS_THETA, numSteps, xmax, r, T, getAssetPrice, payoff, cf);
 }
 
 }  // namespace optionprice

@@ -22,6 +22,9 @@
  *    Like the reference (which validates nothing) NaNs in parameters propagate to the
  *    outputs; only structural errors (null pointers, non power-of-two N, sizes out of the
  *    supported range, unknown enum) are reported.
+ *  - Naming: there are no separate *_async variants of the pricers -- a call whose outputs are all
+ *    device pointers IS asynchronous (previous bullet).  The one explicit *_async entry point,
+ *    fop_gather_losses_async, additionally runs on a side stream.
  *  - A handle is bound to one device and is not thread-safe; use one handle per host thread/GPU.
  *  - There is NO CPU fallback: without a CUDA device fop_create fails with FOP_CUDA_ERROR.
  */
@@ -220,6 +223,13 @@ int fop_calibrate_cf(fop_handle_t h, fop_model_t model, const double* lower, con
 int fop_comm_unique_id(char* id_out128);
 int fop_comm_init(fop_handle_t h, const char* id128, int rank, int world);
 int fop_gather_losses(fop_handle_t h, const double* loss_local, int count, double* loss_all);
+/* Overlapped form (device pointers only): the all-gather is enqueued on a side stream of the handle,
+ * ordered after everything enqueued so far on the handle's stream, and runs beside the kernels the
+ * caller enqueues next (the next calibration step).  fop_comm_wait makes the handle's stream wait
+ * for the last such gather (no host synchronisation).  loss_local / loss_all must stay untouched
+ * until then -- alternate two buffer pairs between steps. */
+int fop_gather_losses_async(fop_handle_t h, const double* loss_local, int count, double* loss_all);
+int fop_comm_wait(fop_handle_t h);
 int fop_comm_destroy(fop_handle_t h);
 
 /* ---- batched FFT (the replacement for fft.hpp:49-61; exposed for parity tests) ---------------
@@ -243,6 +253,34 @@ int fop_fft(fop_handle_t h, double* data, int batch, int N, int inverse);
  */
 int fop_integrate_fft(fop_handle_t h, const double* fn_samples, int batch, int N, double outputMin,
                       double inputMin, double inputMax, int inverse, double* out);
+
+/* ---- caller-sampled characteristic functions / payoffs ------------------------------------------
+ * The reference accepts ANY callable as characteristic function, payoff and asset map
+ * (FangOostGeneric OptionPricing.h:325-333, CarrMadanGeneric :582-590, FSTSGeneric :155-163).  A
+ * callable is only ever evaluated on a grid the library defines, so the host evaluates it there
+ * (the *_u_grid helpers give the points) and hands the samples over; option transform, damping,
+ * weights, transforms, contraction, time stepping, early exercise and the output map run on the
+ * GPU exactly as for the built-in models.  include/fftop/OptionPricing.h wraps these behind the
+ * reference's own signatures taking std::function / lambdas.
+ *
+ * COS:  u_out[numU] = k pi/(x_max - x_min);  cf_samples[P][M][numU][2] = cf_{p,m}(i u_k) (re, im),
+ *       i.e. what the reference's `cf` returns for the complex argument (0, u_k) at maturity T_m.
+ * Carr-Madan: u_out2[N][2] = (alpha + 1, j ada) -- the argument CallAug passes to cf
+ *       (OptionPricing.h:564-567); cf_samples[P][N][2].
+ * FSTS: w_out[N] = getUDomain(vmax, du, k) (OptionPricing.h:19-23), the CF is sampled at (0, w_k) for
+ *       the step length T/steps; payoff[N] (payoff_per_set = 0) or [P][N] = payoff(getAssetPrice(x_j));
+ *       asset[N] = getAssetPrice(x_j), needed for kind delta / gamma only (else NULL).
+ */
+int fop_cos_u_grid(const double* K_desc, int J, double S0, int numU, double* u_out);
+int fop_cos_cf_samples(fop_handle_t h, const double* cf_samples, int P, const double* K_desc, int J,
+                       double S0, double r, const double* T, int M, int numU, int kind, double* out);
+int fop_carr_madan_u_grid(int N, double ada, double alpha, double* u_out2);
+int fop_carr_madan_cf_samples(fop_handle_t h, const double* cf_samples, int P, int N, double ada,
+                              double alpha, double S0, double r, double T, int is_put, double* out);
+int fop_fsts_u_grid(int N, double xmax, double* w_out);
+int fop_fsts_samples(fop_handle_t h, const double* cf_samples, const double* payoff, int payoff_per_set,
+                     const double* asset, int P, int N, double xmax, double r, double T, int steps,
+                     int american, int kind, double* out);
 
 /* measured fp64 FMA throughput of the device in TFLOP/s (roofline denominator, bench.py) */
 int fop_measure_fp64_peak(fop_handle_t h, double* tflops_out);

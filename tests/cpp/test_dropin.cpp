@@ -1,6 +1,7 @@
 // The reference's own test cases (test.cpp) re-expressed against the drop-in headers.
 // Built and run by tests/test_cpp_dropin_gpu.py on a GPU box.
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <deque>
 #include <vector>
@@ -111,6 +112,54 @@ int main() {
       REQUIRE_APPROX(f[m].real(), expect.real(), 1e-9);
       REQUIRE_APPROX(f[m].imag(), expect.imag(), 1e-9);
     }
+  }
+  {  // the reference's OWN call shapes with arbitrary callables (test.cpp:47-79, 342-367, 619-648):
+     // lambdas for the characteristic function, the payoff and the asset map
+    typedef std::complex<double> C;
+    const int numX = 1024;
+    const double xmax = 5.0, K = 50.0, ada = .25;
+    auto BSCF = [&](const C& u) { return std::exp(r * T * u + sig * sig * .5 * T * (u * u - u)); };  // gaussCF, test.cpp:54
+    auto payoff = [&](double assetValue) { return assetValue > K ? assetValue - K : 0.0; };           // test.cpp:56-58
+    auto getAssetPrice = [&](double logAsset) { return K * std::exp(logAsset); };                    // test.cpp:59-61
+    auto fsts = optionprice::FSTSPrice(numX, xmax, r, T, getAssetPrice, payoff, BSCF);
+    auto fstsD = optionprice::FSTSPrice(numX, xmax, r, T, K, fftop::Payoff::Call, fftop::blackScholes(sig));
+    auto S = optionprice::getStrikeUnderlying(-xmax, xmax, K, numX);
+    for (int i = (int)(numX * .3); i < (int)(numX * .7); ++i) {
+      REQUIRE_APPROX(fsts[i], BSCall(S[i], discount, K, sig, T), 1e-4);
+      REQUIRE_APPROX(fsts[i], fstsD[i], 1e-9);     // sampled lambda == on-device model
+    }
+    auto dl = optionprice::FSTSDelta(numX, xmax, r, T, getAssetPrice, payoff, BSCF);
+    auto dlD = optionprice::FSTSDelta(numX, xmax, r, T, K, fftop::Payoff::Call, fftop::blackScholes(sig));
+    for (int i = (int)(numX * .3); i < (int)(numX * .7); ++i) REQUIRE_APPROX(dl[i], dlD[i], 1e-9);
+    // American put through lambdas: 64 steps of the one-step CF
+    const int steps = 64;
+    auto BSCFdt = [&](const C& u) { return std::exp((r * u + sig * sig * .5 * (u * u - u)) * (T / steps)); };
+    auto putPay = [&](double a) { return a < K ? K - a : 0.0; };
+    auto am = optionprice::FSTSPrice(numX, xmax, r, T, getAssetPrice, putPay, BSCFdt, steps, true);
+    auto amD = optionprice::FSTSPrice(numX, xmax, r, T, K, fftop::Payoff::Put, fftop::blackScholes(sig), steps, true);
+    for (int i = (int)(numX * .3); i < (int)(numX * .7); ++i) REQUIRE_APPROX(am[i], amD[i], 1e-9);
+
+    auto cm = optionprice::CarrMadanCall(numX, ada, S0, r, T, BSCF);
+    auto cmD = optionprice::CarrMadanCall(numX, ada, S0, r, T, fftop::blackScholes(sig));
+    for (int i = (int)(numX * .3); i < (int)(numX * .7); ++i) REQUIRE_APPROX(cm[i], cmD[i], 1e-9);
+
+    std::deque<double> Kd = {7500, 60, 50, 40, .3};
+    auto fo = optionprice::FangOostCallPrice(S0, Kd, r, T, 64, BSCF);
+    auto foD = optionprice::FangOostCallPrice(S0, Kd, r, T, 64, fftop::blackScholes(sig));
+    auto foG = optionprice::FangOostCallGamma(S0, Kd, r, T, 64, BSCF);
+    auto foGD = optionprice::FangOostCallGamma(S0, Kd, r, T, 64, fftop::blackScholes(sig));
+    for (int i = 1; i < 4; ++i) {
+      REQUIRE_APPROX(fo[i], BSCall(S0, discount, Kd[i], sig, T), 1e-4);
+      REQUIRE_APPROX(fo[i], foD[i], 1e-10);
+      REQUIRE_APPROX(foG[i], foGD[i], 1e-10);
+    }
+    // helper names of the reference (OptionPricing.h:93-97, 110-117, 121-123)
+    auto x = optionprice::getXFromK(S0, Kd);
+    REQUIRE_APPROX(x[1], std::log(S0 / 60.0), 1e-15);
+    REQUIRE_APPROX(optionprice::getFangOostKAtIndex(-5.0, 10.0 / 1023, S0, 512),
+                   optionprice::getFangOostStrike(-5.0, 5.0, S0, 1024)[512], 1e-15);
+    const double b = optionprice::getMaxK(ada), lambda = optionprice::getLambda(numX, b);
+    REQUIRE_APPROX(optionprice::getCarrMadanKAtIndex(b, lambda, S0, 400), optionprice::getCarrMadanStrikes(ada, S0, numX)[400], 1e-15);
   }
   std::printf(failures ? "FAILED %d\n" : "ALL PASSED\n", failures);
   return failures != 0;

@@ -37,17 +37,17 @@ class HostEmu:
             raise FileNotFoundError("nvcc not available")
         self.lib = C.CDLL(so)
         i, d = C.c_int, C.c_double
-        self.lib.emu_cos.argtypes = [i, i, _dp, i, _dp, i, d, d, _dp, i, i, i, i, _dp]
+        self.lib.emu_cos.argtypes = [i, i, _dp, i, _dp, i, d, d, _dp, i, i, i, i, i, _dp]
         self.lib.emu_logcf.argtypes = [i, i, _dp, d, d, d, d, _dp]
 
-    def cos(self, base, tc, params, K, S0, r, T, numU, kind=0, use_tgrid=True):
+    def cos(self, base, tc, params, K, S0, r, T, numU, kind=0, use_tgrid=True, fast=True):
         K = np.ascontiguousarray(K, dtype=np.float64)
         T = np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
         p = np.ascontiguousarray(params, dtype=np.float64)
         P = p.size // {0: 1, 1: 4, 2: 5}[base] if tc == 0 else p.size // ({0: 1, 1: 4, 2: 5}[base] + 4)
         out = np.empty((P, T.size, K.size))
         rc = self.lib.emu_cos(base, tc, p.ctypes.data_as(_dp), P, K.ctypes.data_as(_dp), K.size, S0, r,
-                              T.ctypes.data_as(_dp), T.size, numU, kind, int(use_tgrid),
+                              T.ctypes.data_as(_dp), T.size, numU, kind, int(use_tgrid), int(fast),
                               out.ctypes.data_as(_dp))
         assert rc == 0
         return out

@@ -20,7 +20,7 @@ using namespace fop;
 
 extern "C" int emu_cos(int base, int tc, const double* params, int P, const double* K_desc, int J,
                        double S0, double r, const double* T, int M, int numU, int kind,
-                       int use_tgrid, double* out) {
+                       int use_tgrid, int fast, double* out) {
   const int np = num_params(base, tc);
   if (np == 0 || J < 2 || M < 1 || numU < 1 || kind < 0 || kind > 7) return 1;
   std::vector<double> Th(T, T + M), x(J), uk(numU), vk(numU);
@@ -34,7 +34,7 @@ extern "C" int emu_cos(int base, int tc, const double* params, int P, const doub
   double dt = 0.0;
   std::vector<int> npow, steps;
   if (use_tgrid && maturity_grid(Th, &dt, &npow)) steps = maturity_steps(npow);
-  else dt = 0.0;
+  if (steps.empty()) dt = 0.0;
   std::vector<double> bc((size_t)numU * J), bs((size_t)numU * J);
   for (int k = 0; k < numU; ++k)
     for (int j = 0; j < J; ++j) {
@@ -62,7 +62,16 @@ extern "C" int emu_cos(int base, int tc, const double* params, int P, const doub
         CfPre pre;
         cf_prepare(base, tc, mc, u, r, pre);
         double2* crow = C.data() + k;
-        if (mode == CF_MODE_CIR) coeff_maturities<CF_MODE_CIR, 2>(a, mc, pre, u, vk[k], crow, Kp);
+        if (mode == CF_MODE_CIR && fast) {  // the specialised kernels' path (cos_coeff_spec.cuh)
+          const int gm = a.greek_mask;
+          if (a.npow) {
+            if (gm == 1) coeff_maturities_g<CF_MODE_CIR, 2, true, 1, true>(a, mc, pre, u, vk[k], crow, Kp);
+            else coeff_maturities_g<CF_MODE_CIR, 2, true, -1, true>(a, mc, pre, u, vk[k], crow, Kp);
+          } else {
+            if (gm == 1) coeff_maturities_g<CF_MODE_CIR, 2, false, 1, true>(a, mc, pre, u, vk[k], crow, Kp);
+            else coeff_maturities_g<CF_MODE_CIR, 2, false, -1, true>(a, mc, pre, u, vk[k], crow, Kp);
+          }
+        } else if (mode == CF_MODE_CIR) coeff_maturities<CF_MODE_CIR, 2>(a, mc, pre, u, vk[k], crow, Kp);
         else if (mode == CF_MODE_LEVY) coeff_maturities<CF_MODE_LEVY, 2>(a, mc, pre, u, vk[k], crow, Kp);
         else coeff_maturities<CF_MODE_DET, 1>(a, mc, pre, u, vk[k], crow, Kp);
       }

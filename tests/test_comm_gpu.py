@@ -56,3 +56,32 @@ def test_c_abi_loss_gather_world_1_host_and_device_pointers():
         assert torch.equal(yd, xd)
     finally:
         eng.close()
+
+
+def test_c_abi_async_gather_world_1_double_buffered():
+    """fop_gather_losses_async / fop_comm_wait on one GPU: side-stream gathers of alternating
+    buffer pairs while the handle's stream keeps producing new losses."""
+    import torch
+
+    import fftoptionpricing_b200 as F
+    eng = F.Engine(0)
+    try:
+        eng.comm_init(F.Engine.comm_unique_id(), 0, 1)
+        stream = torch.cuda.ExternalStream(eng.stream_ptr, device=torch.device("cuda:0"))
+        src = [torch.empty(4096, dtype=torch.float64, device="cuda:0") for _ in range(2)]
+        dst = [torch.empty(4096, dtype=torch.float64, device="cuda:0") for _ in range(2)]
+        seen = []
+        with torch.cuda.stream(stream):
+            for i in range(6):
+                b = i & 1
+                src[b].fill_(float(i))              # "loss kernel" of step i on the handle's stream
+                eng.gather_losses_async(src[b], dst[b])
+                if i >= 1:
+                    seen.append(dst[(i - 1) & 1].clone())   # previous gather is complete by now
+            eng.comm_wait()
+            seen.append(dst[5 & 1].clone())
+        torch.cuda.synchronize()
+        for i, t in enumerate(seen):
+            assert float(t.min()) == float(t.max()) == float(i), (i, float(t.min()), float(t.max()))
+    finally:
+        eng.close()

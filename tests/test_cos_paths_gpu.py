@@ -159,3 +159,32 @@ def test_many_and_few_u_terms(numU, engine, best_oracle, monkeypatch):
     got = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, [0.5, 1.0], numU, 0)
     ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, [0.5, 1.0], numU, 0)
     assert_parity(got, ref, what=f"numU={numU}")
+
+
+@pytest.mark.parametrize("variant", ["generic", "shape0", "shape1", "shape2"])
+@pytest.mark.parametrize("T", [ON_GRID, OFF_GRID, DESCENDING], ids=["monthly", "offgrid", "unsorted"])
+def test_coefficient_kernel_variants_match_oracle(variant, T, engine, best_oracle, monkeypatch):
+    """The generic coefficient kernel (term-by-term CIR clock, FOP_COEFF_GENERIC=1) and every CTA
+    shape of the model-specialised one (re-associated clock, cos_coeff_spec.cuh) against the oracle;
+    the specialised shapes must agree with each other bit for bit (same arithmetic, different
+    launch geometry)."""
+    monkeypatch.delenv("FOP_COS_PATH", raising=False)
+    monkeypatch.delenv("FOP_COEFF_GENERIC", raising=False)
+    monkeypatch.delenv("FOP_COEFF_SHAPE", raising=False)
+    if variant == "generic":
+        monkeypatch.setenv("FOP_COEFF_GENERIC", "1")
+    else:
+        monkeypatch.setenv("FOP_COEFF_SHAPE", variant[-1])
+    prm = CASES.heston_batch(301)
+    K = CASES.c5_strikes()
+    got = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.0, T, 256, 0)
+    ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.0, T, 256, 0)
+    assert_parity(got, ref, what=f"coefficient kernel {variant}, M={len(T)}")
+    if variant != "generic":
+        monkeypatch.setenv("FOP_COEFF_SHAPE", "0")
+        base = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.0, T, 256, 0)
+        assert np.array_equal(got, base)
+    else:
+        monkeypatch.delenv("FOP_COEFF_GENERIC", raising=False)
+        spec = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.0, T, 256, 0)
+        assert not np.array_equal(got, spec) and np.abs(got - spec).max() < 1e-8
