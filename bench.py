@@ -449,7 +449,11 @@ def run_ours(args):
         # ---- sustained leg: the same device-resident step for >= args.sustain_seconds
         sustained = None
         if args.sustain_seconds > 0:
-            n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms / args.steps, 1e-3)) + 1)
+            # the same step count on every rank (each step contains a collective)
+            ms_all = torch.tensor([ms], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms_all, op=dist.ReduceOp.MAX)
+            n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / max(float(ms_all[0]) / args.steps, 1e-3)) + 1)
             sampler2 = ClockSampler(local, uuid) if rank == 0 else None
             ms_sus = timed_device(n_sus)
             clocks2 = sampler2.stop() if sampler2 else None

@@ -8,7 +8,7 @@ from ._lib import LIB_PATH, declared_symbols, load_library  # noqa: F401
 from .engine import (  # noqa: F401
     CALL_DELTA, CALL_GAMMA, CALL_PRICE, CALL_THETA, CGMY, FSTS_DELTA, FSTS_GAMMA, FSTS_PRICE,
     FSTS_THETA, GAUSS, MERTON, PAYOFF_CALL, PAYOFF_PUT, PUT_DELTA, PUT_GAMMA, PUT_PRICE, PUT_THETA,
-    TC_CIR, TC_CIR_DIFFUSION, TC_NONE, Engine, FopError, num_params,
+    TC_CIR, TC_CIR_DIFFUSION, TC_NONE, VG, Engine, FopError, num_params,
 )
 
 load_library()

@@ -21,6 +21,7 @@ bool cos_coeff_launch_spec(fop_handle_t h, const CosCoeffArgs& a_in, int grid_bl
   if (a.base == BASE_GAUSS) k = coeff_pick_gauss(a.tc, grid, price_only, shape, &nt);
   else if (a.base == BASE_MERTON) k = coeff_pick_merton(a.tc, grid, price_only, shape, &nt);
   else if (a.base == BASE_CGMY) k = coeff_pick_cgmy(a.tc, grid, price_only, shape, &nt);
+  else if (a.base == BASE_VG) k = coeff_pick_vg(a.tc, grid, price_only, shape, &nt);
   if (!k) return false;
   // sets per CTA: four (set, u) pairs per thread, whole sets only
   a.spb = std::max(1, std::min(COEFF_MAX_SPB, 4 * nt / a.Kp));

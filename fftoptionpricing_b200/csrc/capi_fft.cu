@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "cf_models.cuh"
@@ -188,6 +189,7 @@ struct PrunedGen {
 struct PrunedEpi {
   CmEpi inner;
   int logR, vec2;
+  double ustep, kstep;  // e^{-alpha lambda 256 R}, e^{lambda 256 R}: factor steps of the 4096-point kernel's epilogue
   __device__ void operator()(int p, int k, cd Z) const {
     const int t = p >> (logR - 1), s = 2 * (p & ((1 << (logR - 1)) - 1));
     const int m = (k << logR) + s;
@@ -255,11 +257,276 @@ __global__ void __launch_bounds__(256, 2) cm_pruned4096_kernel(PrunedGen pg, Pru
     __syncthreads();
     load16(sm, 16 * b, 1, x);
     Dft<16, -1>::run(x);
-    // position 16 b + t holds frequency k = (b >> 4) + 16 (b & 15) + 256 t  (digit reversal)
+    // position 16 b + t holds frequency k = (b >> 4) + 16 (b & 15) + 256 t  (digit reversal), i.e.
+    // outputs m = R (k0 + 256 t) + s, + 1.  The undamping factor e^{-alpha(-b + lambda m)} of
+    // OptionPricing.h:605 (and the strike e^{-b + lambda m} of the put, :652) factor over (k0, t, s):
+    // one exp per thread for k0 (outside the transform loop), a running product over t, two exps
+    // per transform for s, s + 1 -- instead of one or two exps per output (which were ~40 % of the
+    // kernel's fp64 instructions).  The running product carries <= 16 roundings (1e-15 relative).
     const int k0 = (b >> 4) + 16 * (b & 15);
+    const CmEpi& ce = pe.inner;
+    const double al = ce.alpha * ce.lambda;
+    const double f0 = fm_exp(-al * s), f1 = fm_exp(-al * (s + 1));
+    const double rk0 = (double)((long long)k0 << logR);
+    double ut = ce.S0 * fm_exp(-ce.alpha * (-ce.b + ce.lambda * rk0)) * ce.ada / (M_PI * 3.0);
+    double kt = 0.0, g0 = 0.0, g1 = 0.0;
+    if (ce.is_put) {
+      g0 = fm_exp(ce.lambda * s);
+      g1 = fm_exp(ce.lambda * (s + 1));
+      kt = ce.S0 * fm_exp(-ce.b + ce.lambda * rk0) * ce.discount;
+    }
+    const double ustep = pe.ustep, kstep = pe.kstep;
+    double* orow = ce.out + (size_t)(ce.idx ? ce.idx[tset] : tset) * ce.N + ((size_t)k0 << logR) + s;
 #pragma unroll
-    for (int t = 0; t < 16; ++t) pe(p, k0 + 256 * t, x[Dft<16, -1>::out(t)]);
+    for (int t = 0; t < 16; ++t) {
+      const cd Z = x[Dft<16, -1>::out(t)];
+      double v0 = Z.x * (ut * f0), v1 = Z.y * (ut * f1);
+      if (ce.is_put) {
+        v0 = v0 - ce.S0 + kt * g0;
+        v1 = v1 - ce.S0 + kt * g1;
+      }
+      double* o = orow + ((size_t)(256 * t) << logR);
+      if (pe.vec2) {
+        *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+      } else {
+        o[0] = v0;
+        o[1] = v1;
+      }
+      ut *= ustep;
+      kt *= kstep;
+    }
     __syncthreads();  // the next transform's first pass overwrites the grid
+  }
+}
+
+// Set-per-CTA version of the L = 4096 pruned transform (FOP_CM_PRUNED=set; an experiment that did not
+// beat the kernel above, kept selectable with its evidence).  ncu on cm_pruned4096_kernel (profiles/r2_cm_pruned_ncu.json): 54 % of
+// the warp samples wait on the global loads of the generator -- every one of the R/2 transforms of
+// a set re-reads the whole 64 KB head (x_j and x_{L-j}) from L2 behind dependent address
+// arithmetic -- and the head itself makes an HBM round trip out of cm_head_kernel.  Here one
+// persistent CTA of 512 threads owns a set: it evaluates the head ONCE into shared memory (the
+// cm_head_kernel arithmetic, no HBM buffer), then its two groups of 256 threads run the R/2
+// transforms two at a time out of shared memory (own FFT grid each, named barriers per group).  In
+// a round the groups produce residues 4r .. 4r + 3 of every frequency: the two 16-byte stores
+// complete a 32-byte sector together.
+// out of line: the CF evaluation gets its own register allocation instead of competing with the
+// transform's 16-point register tile
+__device__ __noinline__ void cm_head_fill(const CmGen& g, const CmAux* ax, int set, cd* head, int L) {
+  for (int j = threadIdx.x; j < L; j += blockDim.x) head[j] = g(ax, set, set, j);
+}
+__global__ void __launch_bounds__(512, 1) cm_pruned4096_set_kernel(CmGen g, PrunedEpi pe, int nsets, int N,
+                                                                   const double2* __restrict__ twN,
+                                                                   const double2* __restrict__ twL) {
+  constexpr int n = 12, L = 1 << n, S0 = L >> 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* head = reinterpret_cast<cd*>(smem_raw);
+  const int grp = threadIdx.x >> 8, b = threadIdx.x & 255;
+  cd* sm = head + L + (size_t)grp * fft_padded_size(L);
+  const int logR = pe.logR, npairs = 1 << (logR - 1);
+  // The generator's twiddle factors that do not depend on the thread -- W_N^{256 t s}, W_N^{256 t},
+  // c_s, c_{s+1} -- sit in shared memory for the whole launch: with ~200 KB of shared memory in use the
+  // L1 is a few KB, and the per-point table reads were L2 round trips (47 % long-scoreboard stalls).
+  cd* twA = head + L + 2 * (size_t)fft_padded_size(L);  // [npairs][16]: W_N^{256 t (2 pair)}
+  cd* twB = twA + (size_t)npairs * 16;                  // [16]:         W_N^{256 t}
+  cd* twC = twB + 16;                                   // [npairs][2]:  c_s, c_{s+1}
+  CmAux* ax = reinterpret_cast<CmAux*>(twC + 2 * (size_t)npairs);
+  for (int i = threadIdx.x; i < npairs * 16; i += 512)
+    twA[i] = tw_load<-1>(twN, (256 * (i & 15) * 2 * (i >> 4)) & (N - 1));
+  if (threadIdx.x < 16) twB[threadIdx.x] = tw_load<-1>(twN, 256 * threadIdx.x);
+  for (int i = threadIdx.x; i < 2 * npairs; i += 512) twC[i] = tw_load<1>(twN, i * L);
+  const cd w0 = tw_load<-1>(twL, b);
+  const cd w1 = tw_load<-1>(twL, (b & 15) * 16);
+  const int base1 = fft_base16(b, 16);
+  const cd wb = tw_load<-1>(twN, b);
+  const int k0 = (b >> 4) + 16 * (b & 15);
+  const CmEpi& ce = pe.inner;
+  auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory"); };
+  for (int set = blockIdx.x; set < nsets; set += gridDim.x) {
+    __syncthreads();  // the previous set's transforms have finished reading the head
+    if (threadIdx.x == 0) g.fill(*ax, set);
+    __syncthreads();
+    cm_head_fill(g, ax, set, head, L);
+    __syncthreads();
+    double* orow_set = ce.out + (size_t)(ce.idx ? ce.idx[set] : set) * ce.N;
+    const double rk0 = (double)((long long)k0 << logR);
+    for (int pair = grp; pair < npairs; pair += 2) {
+      const int s = 2 * pair;
+      const cd wbs = tw_load<-1>(twN, (b * s) & (N - 1));
+      const cd cs0 = twC[s], cs1 = twC[s + 1];
+      cd x[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int j = b + S0 * t;
+        const cd xv = head[j];
+        if (j == 0) {
+          x[t] = mk(xv.x, xv.x);
+          continue;
+        }
+        const cd xr = conj(head[L - j]);
+        const cd w1t = wbs * twA[pair * 16 + t];
+        const cd w2t = w1t * (wb * twB[t]);
+        const cd a = w1t * (xv + cs0 * xr);
+        const cd bb = w2t * (xv + cs1 * xr);
+        x[t] = mk(0.5 * (a.x - bb.y), 0.5 * (a.y + bb.x));
+      }
+      dif16_regs_pow<-1>(x, w0);
+      store16_dft<-1>(sm, b, S0, x);
+      group_sync();
+      load16(sm, base1, 16, x);
+      dif16_regs_pow<-1>(x, w1);
+      store16_dft<-1>(sm, base1, 16, x);
+      group_sync();
+      load16(sm, 16 * b, 1, x);
+      Dft<16, -1>::run(x);
+      // epilogue: factored undamping, see cm_pruned4096_kernel
+      const double al = ce.alpha * ce.lambda;
+      const double f0 = fm_exp(-al * s), f1 = fm_exp(-al * (s + 1));
+      double ut = ce.S0 * fm_exp(-ce.alpha * (-ce.b + ce.lambda * rk0)) * ce.ada / (M_PI * 3.0);
+      double kt = 0.0, g0 = 0.0, g1 = 0.0;
+      if (ce.is_put) {
+        g0 = fm_exp(ce.lambda * s);
+        g1 = fm_exp(ce.lambda * (s + 1));
+        kt = ce.S0 * fm_exp(-ce.b + ce.lambda * rk0) * ce.discount;
+      }
+      double* orow = orow_set + ((size_t)k0 << logR) + s;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const cd Z = x[Dft<16, -1>::out(t)];
+        double v0 = Z.x * (ut * f0), v1 = Z.y * (ut * f1);
+        if (ce.is_put) {
+          v0 = v0 - ce.S0 + kt * g0;
+          v1 = v1 - ce.S0 + kt * g1;
+        }
+        double* o = orow + ((size_t)(256 * t) << logR);
+        if (pe.vec2) {
+          *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+        } else {
+          o[0] = v0;
+          o[1] = v1;
+        }
+        ut *= pe.ustep;
+        kt *= pe.kstep;
+      }
+      group_sync();  // the group's next transform overwrites its grid
+    }
+  }
+}
+
+// Warp-specialised version (FOP_CM_PRUNED=ws; experiment): the same set-per-CTA scheme, but the two halves of the CTA
+// take different ROLES -- 8 producer warps evaluate the head of set i + 1 into the second of two
+// head buffers while 8 consumer warps run the R/2 transforms of set i.  The two phases want
+// different resources (CF evaluation: the fp64 dispatch port; transforms: shared memory, barriers
+// and the scattered 16-byte stores), so side by side they fill each other's stalls instead of
+// alternating as in cm_pruned4096_set_kernel (ncu: 44 % long-scoreboard + 13 % barrier stalls with
+// the phases serialised).  Hand-off through named barriers (full / empty per buffer).
+__global__ void __launch_bounds__(512, 1) cm_pruned4096_ws_kernel(CmGen g, PrunedEpi pe, int nsets, int N,
+                                                                  const double2* __restrict__ twN,
+                                                                  const double2* __restrict__ twL) {
+  constexpr int n = 12, L = 1 << n, S0 = L >> 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd* head = reinterpret_cast<cd*>(smem_raw);                    // [2][L]
+  cd* sm = head + 2 * L;                                         // FFT grid (padded)
+  const int logR = pe.logR, npairs = 1 << (logR - 1);
+  cd* twA = sm + fft_padded_size(L);                             // [npairs][16]: W_N^{256 t (2 pair)}
+  cd* twB = twA + (size_t)npairs * 16;                           // [16]:         W_N^{256 t}
+  cd* twC = twB + 16;                                            // [npairs][2]:  c_s, c_{s+1}
+  CmAux* ax = reinterpret_cast<CmAux*>(twC + 2 * (size_t)npairs);  // [2]
+  const int role = threadIdx.x >> 8, b = threadIdx.x & 255;
+  for (int i = threadIdx.x; i < npairs * 16; i += 512)
+    twA[i] = tw_load<-1>(twN, (256 * (i & 15) * 2 * (i >> 4)) & (N - 1));
+  if (threadIdx.x < 16) twB[threadIdx.x] = tw_load<-1>(twN, 256 * threadIdx.x);
+  for (int i = threadIdx.x; i < 2 * npairs; i += 512) twC[i] = tw_load<1>(twN, i * L);
+  __syncthreads();
+  const int nloc = (nsets - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // named barriers: 1, 2 = full[buf] (256 arrive + 256 sync), 3, 4 = empty[buf], 5 = producers, 6 = consumers
+  auto bar_sync = [](int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); };
+  auto bar_arrive = [](int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); };
+  if (role == 1) {  // ---- producers: head of set i into head[i & 1]
+    for (int i = 0; i < nloc; ++i) {
+      const int buf = i & 1, set = blockIdx.x + i * gridDim.x;
+      if (i >= 2) bar_sync(3 + buf, 512);  // the consumers have released this buffer
+      if (b == 0) g.fill(ax[buf], set);
+      bar_sync(5, 256);
+      cd* hb = head + (size_t)buf * L;
+      for (int j = b; j < L; j += 256) hb[j] = g(&ax[buf], set, set, j);
+      bar_arrive(1 + buf, 512);
+    }
+    return;
+  }
+  // ---- consumers: the R/2 transforms of set i out of head[i & 1]
+  const cd w0 = tw_load<-1>(twL, b);
+  const cd w1 = tw_load<-1>(twL, (b & 15) * 16);
+  const int base1 = fft_base16(b, 16);
+  const cd wb = tw_load<-1>(twN, b);
+  const int k0 = (b >> 4) + 16 * (b & 15);
+  const CmEpi& ce = pe.inner;
+  const double rk0 = (double)((long long)k0 << logR);
+  const double al = ce.alpha * ce.lambda;
+  for (int i = 0; i < nloc; ++i) {
+    const int buf = i & 1, set = blockIdx.x + i * gridDim.x;
+    bar_sync(1 + buf, 512);  // the head is complete
+    const cd* hb = head + (size_t)buf * L;
+    double* orow_set = ce.out + (size_t)(ce.idx ? ce.idx[set] : set) * ce.N;
+    for (int pair = 0; pair < npairs; ++pair) {
+      const int s = 2 * pair;
+      const cd wbs = tw_load<-1>(twN, (b * s) & (N - 1));
+      const cd cs0 = twC[s], cs1 = twC[s + 1];
+      cd x[16];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int j = b + S0 * t;
+        const cd xv = hb[j];
+        if (j == 0) {
+          x[t] = mk(xv.x, xv.x);
+          continue;
+        }
+        const cd xr = conj(hb[L - j]);
+        const cd w1t = wbs * twA[pair * 16 + t];
+        const cd w2t = w1t * (wb * twB[t]);
+        const cd a = w1t * (xv + cs0 * xr);
+        const cd bb = w2t * (xv + cs1 * xr);
+        x[t] = mk(0.5 * (a.x - bb.y), 0.5 * (a.y + bb.x));
+      }
+      if (pair == npairs - 1 && i + 2 < nloc) bar_arrive(3 + buf, 512);  // last read of this head
+      dif16_regs_pow<-1>(x, w0);
+      store16_dft<-1>(sm, b, S0, x);
+      bar_sync(6, 256);
+      load16(sm, base1, 16, x);
+      dif16_regs_pow<-1>(x, w1);
+      store16_dft<-1>(sm, base1, 16, x);
+      bar_sync(6, 256);
+      load16(sm, 16 * b, 1, x);
+      Dft<16, -1>::run(x);
+      // epilogue: factored undamping, see cm_pruned4096_kernel
+      const double f0 = fm_exp(-al * s), f1 = fm_exp(-al * (s + 1));
+      double ut = ce.S0 * fm_exp(-ce.alpha * (-ce.b + ce.lambda * rk0)) * ce.ada / (M_PI * 3.0);
+      double kt = 0.0, g0 = 0.0, g1 = 0.0;
+      if (ce.is_put) {
+        g0 = fm_exp(ce.lambda * s);
+        g1 = fm_exp(ce.lambda * (s + 1));
+        kt = ce.S0 * fm_exp(-ce.b + ce.lambda * rk0) * ce.discount;
+      }
+      double* orow = orow_set + ((size_t)k0 << logR) + s;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const cd Z = x[Dft<16, -1>::out(t)];
+        double v0 = Z.x * (ut * f0), v1 = Z.y * (ut * f1);
+        if (ce.is_put) {
+          v0 = v0 - ce.S0 + kt * g0;
+          v1 = v1 - ce.S0 + kt * g1;
+        }
+        double* o = orow + ((size_t)(256 * t) << logR);
+        if (pe.vec2) {
+          *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+        } else {
+          o[0] = v0;
+          o[1] = v1;
+        }
+        ut *= pe.ustep;
+        kt *= pe.kstep;
+      }
+      bar_sync(6, 256);  // the next transform overwrites the grid
+    }
   }
 }
 
@@ -572,13 +839,39 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
             const int tc = std::min(tb, cnt - t0);
             gg.idx = d_idx + off + t0;
             ee.idx = d_idx + off + t0;
+            // FOP_CM_PRUNED=set | ws: the set-per-CTA experiments (head in shared memory; phases in turn
+            // or warp-specialised).  Measured on config 4 (profiles/r2_cm_pruned_variants.json): 8.9 /
+            // 11.0 ms against 8.5 ms for head kernel + cm_pruned4096_kernel, which stays the default.
+            const char* pv = std::getenv("FOP_CM_PRUNED");
+            if (logL == 12 && logR <= 6 && pv && (!std::strcmp(pv, "set") || !std::strcmp(pv, "ws")) &&
+                !std::getenv("FOP_CM_GENERIC_PRUNED")) {
+              // set-per-CTA kernels: head evaluated into shared memory, no head buffer round trip
+              const double2* twL = nullptr;
+              FOP_TRY(get_twiddles(h, L, &twL));
+              PrunedEpi pe{ee, logR, reinterpret_cast<uintptr_t>(ee.out) % 16 == 0 ? 1 : 0,
+                           std::exp(-alpha * lambda * 256.0 * (double)(1 << logR)),
+                           std::exp(lambda * 256.0 * (double)(1 << logR))};
+              const bool ws = !std::strcmp(pv, "ws");
+              const size_t smem = (ws ? (2 * (size_t)L + (size_t)fft_padded_size(L)) : ((size_t)L + 2 * (size_t)fft_padded_size(L))) * sizeof(cd) +
+                                  2 * sizeof(CmAux) + ((size_t)(16 + 2) * (1 << (logR - 1)) + 16) * sizeof(cd);
+              auto kern = ws ? cm_pruned4096_ws_kernel : cm_pruned4096_set_kernel;
+              FOP_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              {
+                ProfScope ps(h, ws ? "carr_madan_pruned_ws_kernel" : "carr_madan_pruned_set_kernel");
+                kern<<<std::min(tc, h->sm_count), 512, smem, h->stream>>>(gg, pe, tc, N, twN, twL);
+              }
+              FOP_LAUNCH_CHECK(h);
+              continue;
+            }
             {
               ProfScope ps(h, "carr_madan_head_kernel");
               cm_head_kernel<<<tc, 256, 0, h->stream>>>(gg, L, xbuf);
             }
             FOP_LAUNCH_CHECK(h);
             PrunedGen pg{xbuf, twN, L, logR, N};
-            PrunedEpi pe{ee, logR, reinterpret_cast<uintptr_t>(ee.out) % 16 == 0 ? 1 : 0};
+            PrunedEpi pe{ee, logR, reinterpret_cast<uintptr_t>(ee.out) % 16 == 0 ? 1 : 0,
+                         std::exp(-alpha * lambda * 256.0 * (double)(1 << logR)),
+                         std::exp(lambda * 256.0 * (double)(1 << logR))};
             const int batch = tc << (logR - 1);  // two residue classes per transform
             if (logL == 12 && !std::getenv("FOP_CM_GENERIC_PRUNED")) {
               const double2* twL = nullptr;

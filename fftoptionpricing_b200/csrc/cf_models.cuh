@@ -7,6 +7,9 @@
 //   mertonLogRNCF(u,l,mJ,sJ,r,s)= gaussLogCF(u, r - s^2/2 - l(e^{mJ+sJ^2/2}-1), s) + l(e^{u mJ+sJ^2u^2/2}-1)
 //   cgmyLogRNCF(u,C,G,M,Y,r,s)  = gaussLogCF(u, r - s^2/2 - k(1), s) + k(u),
 //                                 k(u) = C Gamma(-Y)[(M-u)^Y + (G+u)^Y - M^Y - G^Y]  (0 if C == 0)
+//   vgLogRNCF(u,s,th,nu,r)      = u (r + log(1 - th nu - s^2 nu/2)/nu) - log(1 - u th nu - s^2 nu u^2/2)/nu
+//                                 (variance gamma: named by BASELINE.json's north_star, absent from the
+//                                 reference -> textbook form, parity unpinned; no Brownian part)
 //   cirLogMGF(psi,a,kap,sv,t,v0)= -b v0 - c, delta = sqrt(kap^2 + 2 psi sv^2), e = exp(-delta t),
 //                                 b = 2 psi (1-e)/(delta+kap+(delta-kap)e),
 //                                 c = (a/sv^2)[2 log(1-(delta-kap)(1-e)/(2 delta)) + (delta-kap) t]
@@ -21,11 +24,11 @@
 
 namespace fop {
 
-enum { BASE_GAUSS = 0, BASE_MERTON = 1, BASE_CGMY = 2 };
+enum { BASE_GAUSS = 0, BASE_MERTON = 1, BASE_CGMY = 2, BASE_VG = 3 };
 enum { TC_NONE = 0, TC_CIR = 1, TC_CIR_DIFFUSION = 2 };
 
 __host__ __device__ __forceinline__ int num_base_params(int base) {
-  return base == BASE_GAUSS ? 1 : base == BASE_MERTON ? 4 : base == BASE_CGMY ? 5 : 0;
+  return base == BASE_GAUSS ? 1 : base == BASE_MERTON ? 4 : base == BASE_CGMY ? 5 : base == BASE_VG ? 3 : 0;
 }
 __host__ __device__ __forceinline__ int num_params(int base, int tc) {
   const int nb = num_base_params(base);
@@ -38,7 +41,7 @@ struct ModelConsts {
   double sigma, hs2;          // sigma, sigma^2/2
   double comp;                // jump compensator per unit time: lambda(E e^J - 1) or k(1)
   double lam, muJ, hsJ2;      // Merton
-  double cg, G, M, Y, myGy;   // CGMY: cg = C Gamma(-Y), myGy = M^Y + G^Y
+  double cg, G, M, Y, myGy;   // CGMY: cg = C Gamma(-Y), myGy = M^Y + G^Y;  VG: cg = 1/nu, G = theta nu, M = sigma^2 nu/2
   double speed, adaV, v0, aos2, kap1;  // CIR: aos2 = speed/adaV^2, kappa(u) = speed - kap1 u
 };
 
@@ -64,6 +67,13 @@ __host__ __device__ __forceinline__ void make_consts(int base, int tc, const dou
       c.myGy = pow(c.M, c.Y) + pow(c.G, c.Y);
       c.comp = c.cg * (pow(c.M - 1.0, c.Y) + pow(c.G + 1.0, c.Y) - c.myGy);
     }
+  } else if (base == BASE_VG) {  // params [sigma, theta, nu]; pure jump: no Brownian part
+    c.cg = 1.0 / p[2];
+    c.G = p[1] * p[2];
+    c.M = 0.5 * p[0] * p[0] * p[2];
+    c.comp = -c.cg * log(1.0 - c.G - c.M);
+    c.sigma = 0.0;
+    c.hs2 = 0.0;
   }
   c.speed = c.adaV = c.v0 = c.aos2 = c.kap1 = 0.0;
   if (tc != TC_NONE) {
@@ -89,6 +99,11 @@ __host__ __device__ __forceinline__ cd jump_exponent(int base, const ModelConsts
     const cd a = cpow(mk(c.M - u.x, -u.y), c.Y);
     const cd b = cpow(mk(c.G + u.x, u.y), c.Y);
     return mk(c.cg * (a.x + b.x - c.myGy), c.cg * (a.y + b.y));
+  }
+  if (base == BASE_VG) {  // -(1/nu) log(1 - u theta nu - sigma^2 nu u^2 / 2)
+    const cd uu = u * u;
+    const cd l = clog(mk(1.0 - u.x * c.G - c.M * uu.x, -u.y * c.G - c.M * uu.y));
+    return mk(-c.cg * l.x, -c.cg * l.y);
   }
   return mk(0.0, 0.0);
 }

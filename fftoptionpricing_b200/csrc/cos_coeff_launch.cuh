@@ -44,5 +44,6 @@ CoeffKernel coeff_pick_base(int tc, bool grid, bool price_only, int shape, int* 
 CoeffKernel coeff_pick_gauss(int tc, bool grid, bool price_only, int shape, int* nt);
 CoeffKernel coeff_pick_merton(int tc, bool grid, bool price_only, int shape, int* nt);
 CoeffKernel coeff_pick_cgmy(int tc, bool grid, bool price_only, int shape, int* nt);
+CoeffKernel coeff_pick_vg(int tc, bool grid, bool price_only, int shape, int* nt);
 
 }  // namespace fop

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 
-GAUSS, MERTON, CGMY = 0, 1, 2
+GAUSS, MERTON, CGMY, VG = 0, 1, 2, 3
 TC_NONE, TC_CIR, TC_CIR_DIFFUSION = 0, 1, 2
 CALL_PRICE, PUT_PRICE, CALL_DELTA, PUT_DELTA, CALL_GAMMA, PUT_GAMMA, CALL_THETA, PUT_THETA = range(8)
 FSTS_PRICE, FSTS_DELTA, FSTS_GAMMA, FSTS_THETA = range(4)

@@ -10,7 +10,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .engine import CGMY, GAUSS, MERTON, TC_CIR, TC_CIR_DIFFUSION, TC_NONE, num_params
+from .engine import CGMY, GAUSS, MERTON, TC_CIR, TC_CIR_DIFFUSION, TC_NONE, VG, num_params
 
 
 @dataclass
@@ -41,6 +41,12 @@ def merton(sigma, lam, muJ, sigJ) -> CF:
 def cgmy(sigma, C, G, M, Y) -> CF:
     """exp(cgmyLogRNCF(u, C, G, M, Y, r, sigma) T)   (test.cpp:731)"""
     return CF(CGMY, TC_NONE, np.column_stack(np.broadcast_arrays(*map(np.atleast_1d, (sigma, C, G, M, Y)))))
+
+
+def variance_gamma(sigma, theta, nu) -> CF:
+    """exp(vgLogRNCF(u, sigma, theta, nu, r) T): variance gamma (named by the north star; not in the
+    reference -- textbook form, see include/fftop_b200.h)."""
+    return CF(VG, TC_NONE, np.column_stack(np.broadcast_arrays(*map(np.atleast_1d, (sigma, theta, nu)))))
 
 
 def heston(sigma, speed, adaV, rho, v0Hat) -> CF:

@@ -67,6 +67,8 @@ inline CF merton(double sigma, double lambda, double muJ, double sigJ) {
 inline CF cgmy(double sigma, double C, double G, double M, double Y) {
   return {{FOP_CGMY, FOP_TC_NONE}, {sigma, C, G, M, Y}};
 }
+// variance gamma (not in the reference: include/fftop_b200.h, FOP_VG)
+inline CF varianceGamma(double sigma, double theta, double nu) { return {{FOP_VG, FOP_TC_NONE}, {sigma, theta, nu}}; }
 // CIR time change of a Levy base (test.cpp:887-905); GAUSS base = the reference's Heston
 inline CF timeChanged(CF base, double speed, double adaV, double rho, double v0Hat,
                       bool diffusionOnly = false) {

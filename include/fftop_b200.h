@@ -53,6 +53,10 @@ enum fop_status {
  *   FOP_GAUSS  params [sigma]                    gaussLogCF(u, r-sigma^2/2, sigma)      test.cpp:570
  *   FOP_MERTON params [sigma, lambda, muJ, sigJ] mertonLogRNCF(u,lambda,muJ,sigJ,r,sigma) test.cpp:1119
  *   FOP_CGMY   params [sigma, C, G, M, Y]        cgmyLogRNCF(u,C,G,M,Y,r,sigma)         test.cpp:731
+ *   FOP_VG     params [sigma, theta, nu]          vgLogRNCF(u,sigma,theta,nu,r) = u (r + log(1 - theta nu
+ *                                                 - sigma^2 nu/2)/nu) - log(1 - u theta nu - sigma^2 nu u^2/2)/nu
+ *              (variance gamma: named by the north star next to CGMY, NOT in the reference -- textbook
+ *              form, parity unpinned; it has no Brownian part, so a time change acts with rho = 0)
  * Time change (4 more params appended: [speed, adaV, rho, v0Hat]):
  *   FOP_TC_NONE           phi(u) = exp(psi_r(u) T)
  *   FOP_TC_CIR            phi(u) = exp(r T u + cirLogMGF(-psi_0(u), speed, speed-adaV rho u sigma,
@@ -62,7 +66,7 @@ enum fop_status {
  *                                                                           test.cpp:896-905
  * Parameter order follows generateCharts.cpp:215,260,306,346.
  */
-enum fop_base_model { FOP_GAUSS = 0, FOP_MERTON = 1, FOP_CGMY = 2 };
+enum fop_base_model { FOP_GAUSS = 0, FOP_MERTON = 1, FOP_CGMY = 2, FOP_VG = 3 };
 enum fop_time_change { FOP_TC_NONE = 0, FOP_TC_CIR = 1, FOP_TC_CIR_DIFFUSION = 2 };
 
 typedef struct fop_model_s {

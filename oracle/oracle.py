@@ -22,7 +22,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libfftop_oracle_ref.so")
 PORT_SO = os.path.join(_HERE, "libfftop_oracle_port.so")
 
-GAUSS, MERTON, CGMY = 0, 1, 2
+GAUSS, MERTON, CGMY, VG = 0, 1, 2, 3
 TC_NONE, TC_CIR, TC_CIR_DIFFUSION = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -40,7 +40,7 @@ def _arr(a, shape=None) -> np.ndarray:
 
 
 def num_params(base: int, tc: int) -> int:
-    nb = {0: 1, 1: 4, 2: 5}.get(base, 0)
+    nb = {0: 1, 1: 4, 2: 5, 3: 3}.get(base, 0)
     if nb == 0 or tc not in (0, 1, 2):
         return 0
     return nb + (0 if tc == 0 else 4)

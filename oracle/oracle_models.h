@@ -13,7 +13,7 @@
 namespace oramodel {
 typedef std::complex<double> cplx;
 
-inline int numBase(int base) { return base == 0 ? 1 : base == 1 ? 4 : base == 2 ? 5 : 0; }
+inline int numBase(int base) { return base == 0 ? 1 : base == 1 ? 4 : base == 2 ? 5 : base == 3 ? 3 : 0; }
 inline int numParams(int base, int tc) {
   const int nb = numBase(base);
   if (nb == 0 || tc < 0 || tc > 2) return 0;
@@ -30,12 +30,13 @@ struct Model {
     switch (base) {
       case 0: return chfunctions::gaussLogCF(u, rate - sig * sig * .5, sig);       // test.cpp:570
       case 1: return chfunctions::mertonLogRNCF(u, p[1], p[2], p[3], rate, sig);   // test.cpp:1119
-      default: return chfunctions::cgmyLogRNCF(u, p[1], p[2], p[3], p[4], rate, sig);  // :731
+      case 2: return chfunctions::cgmyLogRNCF(u, p[1], p[2], p[3], p[4], rate, sig);  // :731
+      default: return chfunctions::vgLogRNCF(u, p[0], p[1], p[2], rate);  // VG: no diffusion part
     }
   }
   // log of the characteristic function of log(S_T/S_0)
   cplx logCF(const cplx& u) const {
-    const double sig = p[0];
+    const double sig = base == 3 ? 0.0 : p[0];  // Brownian volatility (variance gamma has none)
     if (tc == 0) return baseLogRNCF(u, r, sig) * T;
     const double* q = p + numBase(base);
     const double speed = q[0], adaV = q[1], rho = q[2], v0Hat = q[3];

@@ -60,6 +60,20 @@ auto cgmyLogRNCF(const U& u, const Number& C, const Number& G, const Number& M,
          cgmyLogCF(u, C, G, M, Y);
 }
 
+// Variance gamma (BASELINE.json north_star names "CGMY/VG").  NOT in the reference and not in the
+// pinned CharacteristicFunctions revision's call sites: parity UNPINNED -- textbook form (Madan,
+// Carr, Chang 1998), X_t = theta G_t + sigma W(G_t), G a gamma process of variance rate nu:
+//   E e^{u X_t} = (1 - u theta nu - sigma^2 nu u^2 / 2)^(-t/nu)
+// checked against a 40-digit evaluation in tests/mp_exact.py.
+template <typename U, typename Number>
+auto vgLogCF(const U& u, const Number& sigma, const Number& theta, const Number& nu) {
+  return -(1.0 / nu) * log(1.0 - u * theta * nu - 0.5 * sigma * sigma * nu * u * u);
+}
+template <typename U, typename Number>
+auto vgLogRNCF(const U& u, const Number& sigma, const Number& theta, const Number& nu, const Number& r) {
+  return u * (r + std::log(1.0 - theta * nu - 0.5 * sigma * sigma * nu) / nu) + vgLogCF(u, sigma, theta, nu);
+}
+
 // log E[exp(-psi int_0^t v_s ds)],  dv = (a - kappa v) dt + sigma sqrt(v) dW.
 template <typename Psi, typename A, typename Kappa, typename Sigma, typename T, typename V0>
 auto cirLogMGF(const Psi& psi, const A& a, const Kappa& kappa, const Sigma& sigma,

@@ -13,7 +13,7 @@ import math
 
 import numpy as np
 
-GAUSS, MERTON, CGMY = 0, 1, 2
+GAUSS, MERTON, CGMY, VG = 0, 1, 2, 3
 TC_NONE, TC_CIR, TC_CIR_DIFFUSION = 0, 1, 2
 SEED = 20240611
 
@@ -87,6 +87,16 @@ def cgmy_batch(P, seed=SEED):
     y = p[:, 4]
     y[np.abs(y - 1.0) < 0.02] = 1.05
     p[0] = [0.2, 1.0, 1.4, 2.5, 1.4]
+    return p
+
+
+def vg_batch(P, seed=SEED):
+    """(sigma, theta, nu) ~ U([.05,.5]x[-.4,.2]x[.05,.8]); set 0 = Madan-Carr-Chang (.12, -.14, .2)."""
+    rng = np.random.default_rng(seed + 3)
+    lo = np.array([0.05, -0.4, 0.05])
+    hi = np.array([0.5, 0.2, 0.8])
+    p = lo + (hi - lo) * rng.random((P, 3))
+    p[0] = [0.12, -0.14, 0.2]
     return p
 
 

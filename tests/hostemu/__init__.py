@@ -44,7 +44,8 @@ class HostEmu:
         K = np.ascontiguousarray(K, dtype=np.float64)
         T = np.ascontiguousarray(np.atleast_1d(T), dtype=np.float64)
         p = np.ascontiguousarray(params, dtype=np.float64)
-        P = p.size // {0: 1, 1: 4, 2: 5}[base] if tc == 0 else p.size // ({0: 1, 1: 4, 2: 5}[base] + 4)
+        nb = {0: 1, 1: 4, 2: 5, 3: 3}[base]
+        P = p.size // nb if tc == 0 else p.size // (nb + 4)
         out = np.empty((P, T.size, K.size))
         rc = self.lib.emu_cos(base, tc, p.ctypes.data_as(_dp), P, K.ctypes.data_as(_dp), K.size, S0, r,
                               T.ctypes.data_as(_dp), T.size, numU, kind, int(use_tgrid), int(fast),

@@ -27,6 +27,9 @@ def levy_log_rn(base, p, u, rate, sig):
         lam, muJ, sJ = p[1], p[2], p[3]
         comp = lam * (mp.exp(muJ + sJ * sJ / 2) - 1)
         return _gauss_log(u, rate - sig * sig / 2 - comp, sig) + lam * (mp.exp(_gauss_log(u, muJ, sJ)) - 1)
+    if base == 3:  # variance gamma [sigma, theta, nu], textbook (Madan-Carr-Chang 1998); no Brownian part
+        s, th, nu = p[0], p[1], p[2]
+        return u * (rate + mp.log(1 - th * nu - s * s * nu / 2) / nu) - mp.log(1 - u * th * nu - s * s * nu * u * u / 2) / nu
     C, G, M, Y = p[1], p[2], p[3], p[4]
 
     def k(z):
@@ -39,10 +42,10 @@ def levy_log_rn(base, p, u, rate, sig):
 def log_cf(base, tc, params, r, T, u):
     p = [mp.mpf(float(x)) for x in params]
     r, T, u = mp.mpf(float(r)), mp.mpf(float(T)), mp.mpc(u)
-    sig = p[0]
+    sig = mp.mpf(0) if base == 3 else p[0]
     if tc == 0:
         return levy_log_rn(base, p, u, r, sig) * T
-    nb = {0: 1, 1: 4, 2: 5}[base]
+    nb = {0: 1, 1: 4, 2: 5, 3: 3}[base]
     speed, adaV, rho, v0 = p[nb:nb + 4]
     if tc == 1:
         psi = -levy_log_rn(base, p, u, mp.mpf(0), sig)

@@ -53,4 +53,7 @@ def test_shortcut_is_bit_identical(N, model, engine, monkeypatch):
     pruned_put = engine.carr_madan(*args, is_put=True)
     tol = carr_madan_tolerance(full, N, 0.25, 1.5)
     assert_parity_tol(pruned, full, tol, what=f"pruned vs full, {model}, N={N}")
-    assert_parity_tol(pruned_put, full_put, tol, what=f"pruned vs full (put), {model}, N={N}")
+    # the put adds S0 (K_m e^{-rT}/S0 - 1) (OptionPricing.h:652), up to 1e8 at the high-strike end: its
+    # tolerance is relative to the put values, not to the calls'
+    tol_put = np.maximum(tol, carr_madan_tolerance(full_put, N, 0.25, 1.5))
+    assert_parity_tol(pruned_put, full_put, tol_put, what=f"pruned vs full (put), {model}, N={N}")

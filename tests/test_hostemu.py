@@ -76,3 +76,24 @@ def test_emulated_heston_box_edges(emu, best_oracle):
         r_ref = (np.abs(ref[i] - ex) / tol).max()
         r_emu = (np.abs(got[i] - ex) / tol).max()
         assert r_ref > 1.0 and r_emu <= 5.0 * r_ref, (prm[i], r_ref, r_emu)
+
+
+def test_emulated_variance_gamma_vs_oracle_and_40_digit_reference(emu, best_oracle):
+    """FOP_VG (north star "CGMY/VG"; absent from the reference, parity unpinned): the device code
+    against the oracle's shim AND the shim against an independent 40-digit evaluation of the
+    textbook CF."""
+    from tests import mp_exact as MP
+    K = CASES.c5_strikes()
+    T = [.25, 1.0]
+    prm = CASES.vg_batch(40)
+    ref = best_oracle.cos(3, 0, prm, K, 100.0, .05, T, 256, 0)
+    got = emu.cos(3, 0, prm, K, 100.0, .05, T, 256, 0)
+    assert _ratio(got, ref).max() <= 1.0
+    ex = MP.cos_call_prices(3, 0, prm[0], K, 100.0, .05, T, 256)
+    assert (np.abs(ref[0] - ex) / (ATOL + RTOL * np.abs(ex))).max() <= 1.0
+    h = CASES.heston_batch(12)[:, 1:]
+    prm2 = np.hstack([CASES.vg_batch(12), h])
+    for tc in (1, 2):
+        ref = best_oracle.cos(3, tc, prm2, K, 100.0, .05, T, 128, 0)
+        got = emu.cos(3, tc, prm2, K, 100.0, .05, T, 128, 0)
+        assert _ratio(got, ref).max() <= 1.0, tc
