@@ -56,6 +56,10 @@ _SIGNATURES = {
                                    C.c_double, C.c_double, C.c_int, C.c_int, C.c_double,
                                    C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_int)]),
+    "fop_calibrate_cos": (C.c_int, [C.c_void_p, fop_model_t, _dp, _dp, C.c_void_p, C.c_int, C.c_double,
+                                    C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_double, C.c_ulonglong, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.POINTER(C.c_int)]),
     "fop_cos_loss": (C.c_int, [C.c_void_p, fop_model_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -273,6 +273,30 @@ class Engine:
             C.c_void_p(fv.ctypes.data), C.c_void_p(its.ctypes.data), C.byref(best)))
         return prm, fv, its, best.value
 
+    def calibrate_cos(self, base, tc, lower, upper, K_desc, S0, r, T, numU, mkt, w=None, nests=25,
+                      iterations=300, tol=0.0, seed=42, restarts=64):
+        """Population cuckoo search over the PRICE-space objective of ``cos_loss`` (restarts x nests
+        parameter sets priced per half-iteration by the batched COS kernels).  Returns ``(params[restarts,
+        np], fnval[restarts], iterations, best_restart)``."""
+        npar = num_params(base, tc)
+        lo = np.ascontiguousarray(np.asarray(lower, dtype=np.float64))
+        hi = np.ascontiguousarray(np.asarray(upper, dtype=np.float64))
+        assert lo.size == npar and hi.size == npar, (lo.size, hi.size, npar)
+        Kb = _Buf(K_desc)
+        Tb = _Buf(np.atleast_1d(np.asarray(T, dtype=np.float64)))
+        mb, wb = _Buf(mkt), _Buf(w)
+        assert mb.size == Tb.size * Kb.size
+        prm = np.empty((restarts, npar))
+        fv = np.empty(restarts)
+        its = np.empty(restarts, dtype=np.int32)
+        best = C.c_int(0)
+        self._check(self._L.fop_calibrate_cos(
+            self._h, _lib.fop_model_t(base, tc), lo.ctypes.data_as(_lib._dp), hi.ctypes.data_as(_lib._dp),
+            Kb.ptr, Kb.size, float(S0), float(r), Tb.ptr, Tb.size, int(numU), mb.ptr, wb.ptr, int(nests),
+            int(iterations), float(tol), int(seed), int(restarts), C.c_void_p(prm.ctypes.data),
+            C.c_void_p(fv.ctypes.data), C.c_void_p(its.ctypes.data), C.byref(best)))
+        return prm, fv, int(its[0]), best.value
+
     def cos_loss(self, base, tc, params, K_desc, S0, r, T, numU, mkt, w=None, want_prices=False,
                  out=None, prices_out=None):
         pb, P = self._params(base, tc, params)

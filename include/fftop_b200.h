@@ -216,6 +216,20 @@ int fop_calibrate_cf(fop_handle_t h, fop_model_t model, const double* lower, con
                      int iterations, double tol, unsigned long long seed, int restarts,
                      double* params_out, double* fnval_out, int* iters_out, int* best_restart_out);
 
+/* Price-space calibration (SURVEY.md 8f-1 on the objective of fop_cos_loss): the same cuckoo search, the
+ * objective of a candidate is (1/(M J)) sum w_mj (FangOostCallPrice_mj(theta) - mkt_mj)^2.  The
+ * `restarts` searches of `nests` nests form one population of restarts x nests parameter sets that is
+ * priced per half-iteration by the batched COS kernels (use restarts x nests >= ~1e4 to fill the GPU;
+ * 2 <= nests <= 4096).  The tolerance is tested every 16 iterations.  Outputs as fop_calibrate_cf;
+ * fnval_out[i] is bit-identical to fop_cos_loss evaluated at params_out[i] inside the same population
+ * layout.  iters_out[i] = iterations run (the same for every restart).
+ */
+int fop_calibrate_cos(fop_handle_t h, fop_model_t model, const double* lower, const double* upper,
+                      const double* K_desc, int J, double S0, double r, const double* T, int M, int numU,
+                      const double* mkt, const double* w, int nests, int iterations, double tol,
+                      unsigned long long seed, int restarts, double* params_out, double* fnval_out,
+                      int* iters_out, int* best_restart_out);
+
 /* ---- multi-GPU: the one collective of the path -----------------------------------
  * One process per GPU, one handle per process.  Parameter sets are sharded contiguously over the
  * ranks and priced without any exchange; fop_gather_losses all-gathers the per-set losses (NCCL

@@ -6,6 +6,7 @@
 #include <deque>
 #include <vector>
 
+#include "fftop/AffineODE.h"
 #include "fftop/OptionCalibration.h"
 #include "fftop/OptionPricing.h"
 #include "fftop/cuckoo.h"
@@ -160,6 +161,26 @@ int main() {
                    optionprice::getFangOostStrike(-5.0, 5.0, S0, 1024)[512], 1e-15);
     const double b = optionprice::getMaxK(ada), lambda = optionprice::getLambda(numX, b);
     REQUIRE_APPROX(optionprice::getCarrMadanKAtIndex(b, lambda, S0, 400), optionprice::getCarrMadanStrikes(ada, S0, numX)[400], 1e-15);
+  }
+  {  // ODE-based characteristic function of the calibration driver (generateCharts.cpp:391-439): Riccati
+     // system solved by 64 Runge-Kutta steps on the host, priced on the GPU through the callable overload.
+     // lambda = 0 must reduce to the CIR time change = the on-device Heston model (test.cpp:1033-1068).
+    typedef std::complex<double> C;
+    const double b = .0398, a = 1.5768, c = .5751, rho = -.5711, v0 = .0175;   // test.cpp:1035-1048
+    const double sigma = std::sqrt(b), speed = a, adaV = c / std::sqrt(b), v0Hat = v0 / b, Tm = 1.0;
+    const auto lcf = fftop::cfLogGeneric(Tm)(0.0, -.05, .1, sigma, v0Hat, speed, adaV, rho, .2);
+    auto cf = [&](const C& u) { return std::exp(lcf(u)); };       // r = 0 as in the reference's Heston test
+    std::vector<double> K = {5000, 120, 100, 80, .3};
+    auto ode = optionprice::FangOostCallPrice(100.0, K, 0.0, Tm, 256, cf);
+    auto dev = optionprice::FangOostCallPrice(100.0, K, 0.0, Tm, 256, fftop::heston(sigma, speed, adaV, rho, v0Hat));
+    for (int i = 1; i < 4; ++i) REQUIRE_APPROX(ode[i], dev[i], 2e-7);     // RK4, 64 steps
+    REQUIRE_APPROX(dev[2], 5.78515545, 1e-4);                              // test.cpp:1065
+    // with volatility jumps the model stays a martingale: phi(1) = 1 (r = 0), and prices move
+    const auto lj = fftop::cfLogGeneric(Tm)(.3, -.05, .1, sigma, v0Hat, speed, adaV, rho, .2);
+    REQUIRE_APPROX(std::abs(std::exp(lj(C(1.0, 0.0)))), 1.0, 1e-6);
+    auto cfj = [&](const C& u) { return std::exp(lj(u)); };
+    auto odej = optionprice::FangOostCallPrice(100.0, K, 0.0, Tm, 256, cfj);
+    if (!(odej[2] > ode[2] + 1e-3)) { std::printf("FAIL jumps should add value: %g vs %g\n", odej[2], ode[2]); ++failures; }
   }
   std::printf(failures ? "FAILED %d\n" : "ALL PASSED\n", failures);
   return failures != 0;
