@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "cos_fused_ws.cuh"
+#include "cos_gemm_tma.cuh"
 #include "cos_gemm_variants.h"
 #include "cos_host_tables.h"
 #include "handle.cuh"
@@ -32,6 +33,45 @@ const GemmExVariant* pick_gemm_ex(int J) {
     if (J == 8 * t[i].NB + t[i].EX) return &t[i];
   return nullptr;
 }
+// ---- TMA tensor maps for the contraction (cos_gemm_tma.cuh); the driver entry point is resolved
+// through the runtime, so the library still links against cudart only
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = []() -> TmapEncodeFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<TmapEncodeFn>(p);
+  }();
+  return fn;
+}
+// fp64 matrix [dim1][dim0] (dim0 contiguous, row pitch `pitch` doubles), boxes of box1 x box0
+bool make_tmap_2d(CUtensorMap* m, const double* base, unsigned long long dim0, unsigned long long dim1,
+                  unsigned long long pitch, unsigned box0, unsigned box1, bool swizzle128) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {dim0, dim1};
+  const cuuint64_t strides[1] = {pitch * 8};
+  const cuuint32_t box[2] = {box0, box1};
+  const cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+const GemmTmaVariant* pick_gemm_tma(int NB, int EX) {
+  if (const char* e = std::getenv("FOP_GEMM_TMA"))
+    if (e[0] == '0') return nullptr;
+  int n = 0;
+  const GemmTmaVariant* t = fop::gemm_tma_variants(&n);
+  for (int i = 0; i < n; ++i)
+    if (t[i].NB == NB && t[i].EX == EX) return &t[i];
+  return nullptr;
+}
+
 // strike-block width that wastes the fewest padded columns (ties -> wider block)
 const GemmVariant* pick_gemm(int J, int* nblk_out) {
   const GemmVariant* best = nullptr;
@@ -206,6 +246,18 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   auto gemm_kernel = gx ? gx->kern : mb == 2 ? gv->dmma2 : gv->dmma4;
   const size_t gemm_smem = cos_dmma_smem(gx ? gx->NB : gv->NB);
   FOP_CUDA(h, cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+  // default: operands by TMA into an mbarrier ring (cos_gemm_tma.cuh); FOP_GEMM_TMA=0 / FOP_GEMM_MB=2:
+  // the cp.async kernels above
+  const int g_nb = gx ? gx->NB : gv->NB, g_ex = gx ? gx->EX : 0;
+  const GemmTmaVariant* gt = (!fused && mb == 4 && tmap_encoder()) ? pick_gemm_tma(g_nb, g_ex) : nullptr;
+  CUtensorMap tmB;
+  if (gt) {
+    if (!make_tmap_2d(&tmB, d_basis, (unsigned long long)Jp, (unsigned long long)KK, (unsigned long long)Jp,
+                      (unsigned)dm_bs(g_nb), TM_KC, false))
+      gt = nullptr;
+    else
+      FOP_CUDA(h, cudaFuncSetAttribute(gt->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cos_tma_smem(g_nb)));
+  }
 
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
     const int pc = (int)std::min<long long>(chunkP, P - p0);
@@ -284,10 +336,29 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ga.mvec2 = (J % 2 == 0) && (JB % 2 == 0) && (reinterpret_cast<uintptr_t>(d_mkt) % 16 == 0) &&
                  (reinterpret_cast<uintptr_t>(d_w) % 16 == 0);
       ga.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
+      ga.tab_smem = 0;
       const dim3 ggrid((unsigned)((rows + DM_RT - 1) / DM_RT), (unsigned)nblk);
+      CUtensorMap tmA;
+      const bool use_tma = gt && make_tmap_2d(&tmA, ga.C, (unsigned long long)KK, (unsigned long long)rows,
+                                              (unsigned long long)KK, TM_KC, DM_RT, true);
       {
         ProfScope ps(h, "cos_gemm_kernel");
-        gemm_kernel<<<ggrid, 32 * (DM_RT / (8 * mb)), gemm_smem, h->stream>>>(ga);
+        if (use_tma) {  // persistent: two CTAs per SM (FOP_GEMM_TMA_CTAS=n: per SM, A/B runs)
+          int per_sm = 2;
+          if (const char* e = std::getenv("FOP_GEMM_TMA_CTAS")) per_sm = std::max(1, atoi(e));
+          const dim3 pgrid((unsigned)std::min<long long>(ggrid.x, (long long)h->sm_count * per_sm), (unsigned)nblk);
+          // market / weight tables in shared memory when two CTAs per SM still fit (227 KB - 1 KB
+          // reserved per CTA, ~2.2 KB static)
+          size_t smem = cos_tma_smem(g_nb);
+          const size_t tabb = cos_tma_tab_bytes(g_nb, M);
+          if (loss && d_mkt && 2 * (smem + tabb + 3400) <= h->smem_optin_sm && !std::getenv("FOP_GEMM_NO_TAB")) {
+            ga.tab_smem = 1;
+            smem += tabb;
+            FOP_CUDA(h, cudaFuncSetAttribute(gt->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          }
+          gt->kern<<<pgrid, 128, smem, h->stream>>>(ga, tmA, tmB);
+        }
+        else gemm_kernel<<<ggrid, 32 * (DM_RT / (8 * mb)), gemm_smem, h->stream>>>(ga);
       }
       FOP_LAUNCH_CHECK(h);
       if (out_host)

@@ -118,6 +118,7 @@ struct CosGemmArgs {
   double* rowloss;        // [rows][nblk] or nullptr
   int vec2;               // prices may be stored as 16-byte pairs (J even, out 16-byte aligned)
   int mvec2;              // mkt / w may be loaded as 16-byte pairs (J even, tables 16-byte aligned)
+  int tab_smem;           // TMA kernel: market / weight tables staged in shared memory
 };
 
 // ---------------------------------------------------------------------------------------------
