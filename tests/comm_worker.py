@@ -41,6 +41,17 @@ def main():
     gathered = eng.gather_losses(local).reshape(world, cap)
     full = np.concatenate([gathered[r, : calibration.shard_bounds(P, r, world)[1] - calibration.shard_bounds(P, r, world)[0]]
                            for r in range(world)])
+    # overlapped form: device buffers, side stream, two alternating buffer pairs
+    import torch
+    dev = torch.device(f"cuda:{rank}")
+    lt = [torch.tensor(local, device=dev) * (k + 1) for k in range(2)]
+    gt = [torch.empty(world * cap, dtype=torch.float64, device=dev) for _ in range(2)]
+    for k in range(4):
+        eng.gather_losses_async(lt[k & 1], gt[k & 1])
+    eng.comm_wait()
+    eng.synchronize()
+    for k in range(2):
+        assert np.array_equal(gt[k].cpu().numpy().reshape(world, cap), gathered * (k + 1)), "async gather mismatch"
     out = {"rank": rank, "full": full.tolist()}
     if rank == 0:
         out["single"] = eng.cos_loss(F.GAUSS, F.TC_CIR, prm, K, 100.0, 0.0, T, 256, mkt, w).tolist()
