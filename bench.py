@@ -273,7 +273,7 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def extra_configs(eng, torch, dev, peak):
+def extra_configs(eng, torch, dev, peak, stream):
     """The other BASELINE.json configs (C2, C3 at P = 4096, C4 at P = 16384) on one GPU, device
     resident, timed per kernel with the library's CUDA-event profiling: driver-observed lines for
     the kernels the headline workload does not touch.  Roofline per SURVEY.md 8d."""
@@ -281,23 +281,32 @@ def extra_configs(eng, torch, dev, peak):
     out = {}
 
     def timed(fn, reps):
+        """(wall ms per call by CUDA events on the handle's stream, per-kernel ms from a separate
+        profiled pass -- kernels of one call may overlap on side streams, so their sum can exceed the wall)"""
         fn()
         fn()
         eng.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        wall = e0.elapsed_time(e1) / reps
         eng.profile_enable(True)
         for _ in range(reps):
             fn()
         prof = eng.profile_read()
         eng.profile_enable(False)
-        return {k: v[0] / reps for k, v in prof.items()}
+        return wall, {k: v[0] / reps for k, v in prof.items()}
 
     # C2: Heston COS, 256 u x 1024 strikes, one maturity (batch of 4096 sets)
     P = 4096
     prm = torch.tensor(CASES.heston_batch(P), device=dev)
     K = CASES.fang_oost_strikes(-5.0, 5.0, 100.0, 1024)
     o = torch.empty((P, 1, 1024), dtype=torch.float64, device=dev)
-    k = timed(lambda: eng.cos(F.GAUSS, F.TC_CIR, prm, K, 100.0, 0.0, [1.0], 256, 0, out=o), 5)
-    ms = sum(k.values())
+    ms, k = timed(lambda: eng.cos(F.GAUSS, F.TC_CIR, prm, K, 100.0, 0.0, [1.0], 256, 0, out=o), 5)
     fl = P * 1024 * 4.0 * 256
     out["C2"] = {"workload": f"Heston COS 256 u x 1024 strikes x {P} sets", "ms": ms, "kernels_ms": k,
                  "value": P * 1024 / (ms * 1e-3), "unit": UNIT,
@@ -309,9 +318,8 @@ def extra_configs(eng, torch, dev, peak):
     P = 4096
     prm = torch.tensor(CASES.merton_batch(P), device=dev)
     o = torch.empty((P, 4096), dtype=torch.float64, device=dev)
-    k = timed(lambda: eng.fsts(F.MERTON, 0, prm, 4096, 7.5, 100.0, .05, .25, steps=256, american=True,
-                               payoff=1, out=o), 3)
-    ms = sum(k.values())
+    ms, k = timed(lambda: eng.fsts(F.MERTON, 0, prm, 4096, 7.5, 100.0, .05, .25, steps=256, american=True,
+                                   payoff=1, out=o), 3)
     fl = P * (256 * (2 * 5 * 4096 * 12 + 8 * 4096.0))
     out["C3"] = {"workload": f"Merton American put FSTS 2^12 nodes x 256 steps x {P} sets", "ms": ms,
                  "kernels_ms": k, "value": P * 4096 / (ms * 1e-3), "unit": UNIT,
@@ -323,8 +331,7 @@ def extra_configs(eng, torch, dev, peak):
     P = 16384
     prm = torch.tensor(CASES.cgmy_batch(P), device=dev)
     o = torch.empty((P, 65536), dtype=torch.float64, device=dev)
-    k = timed(lambda: eng.carr_madan(F.CGMY, 0, prm, 65536, .25, 1.5, 500.0, .4, .25, False, out=o), 3)
-    ms = sum(k.values())
+    ms, k = timed(lambda: eng.carr_madan(F.CGMY, 0, prm, 65536, .25, 1.5, 500.0, .4, .25, False, out=o), 3)
     by = P * 65536 * 8.0
     hbm = measured_peaks().get("hbm_gbs", 6554.6)
     out["C4"] = {"workload": f"CGMY Carr-Madan 2^16 points x {P} sets, all strikes", "ms": ms, "kernels_ms": k,
@@ -499,7 +506,7 @@ def run_ours(args):
                       "unit": UNIT}
             del prm_g, loss_g, prices_g
             torch.cuda.empty_cache()
-            extra = extra_configs(eng, torch, dev, max(peaks[0], peaks[1]))
+            extra = extra_configs(eng, torch, dev, max(peaks[0], peaks[1]), stream)
 
     # max over ranks
     sus_ms = sustained[1] if sustained else 0.0

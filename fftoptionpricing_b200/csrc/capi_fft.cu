@@ -211,17 +211,8 @@ struct PrunedEpi {
 // registers, so the grid makes two shared-memory round trips instead of four and the digit-reversed
 // (bank-conflicting) epilogue read disappears.  One transform (= two residue classes of one set)
 // per CTA of 256 threads.
-// TMA_STORE (FOP_CM_PRUNED=tma): the outputs of a transform are the residue pairs (s, s + 1) of every
-// frequency k -- 16 bytes at a 128-byte stride.  Per-thread stores touch 32 sectors per warp
-// instruction and the next transform's registers wait for them (54 % long-scoreboard stalls).  Here
-// the epilogue writes its values into the (now free) FFT grid in natural k order -- rows of 16
-// frequencies, 256 bytes, behind the grid's usual 16-byte row padding -- and every thread hands ONE row
-// to the TMA unit as a {2, 16, 1} box of the 3-D tensor out[set][k][s]: the strided writes leave
-// through the async proxy while the threads go on to the next transform's generator.
-template <bool TMA_STORE>
 __global__ void __launch_bounds__(256, 2) cm_pruned4096_kernel(PrunedGen pg, PrunedEpi pe, int batch,
-                                                               const double2* __restrict__ twL,
-                                                               const __grid_constant__ CUtensorMap tmOut) {
+                                                               const double2* __restrict__ twL) {
   constexpr int n = 12, L = 1 << n, S0 = L >> 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* sm = reinterpret_cast<cd*>(smem_raw);
@@ -296,31 +287,15 @@ __global__ void __launch_bounds__(256, 2) cm_pruned4096_kernel(PrunedGen pg, Pru
         v0 = v0 - ce.S0 + kt * g0;
         v1 = v1 - ce.S0 + kt * g1;
       }
-      if (TMA_STORE) {
-        sm[fft_pad(k0 + 256 * t)] = mk(v0, v1);
+      double* o = orow + ((size_t)(256 * t) << logR);
+      if (pe.vec2) {
+        *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
       } else {
-        double* o = orow + ((size_t)(256 * t) << logR);
-        if (pe.vec2) {
-          *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
-        } else {
-          o[0] = v0;
-          o[1] = v1;
-        }
+        o[0] = v0;
+        o[1] = v1;
       }
       ut *= ustep;
       kt *= kstep;
-    }
-    if (TMA_STORE) {
-      // generic-proxy writes -> visible to the async proxy, all rows complete, then one box per thread
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncthreads();
-      const int row = pe.inner.idx ? pe.inner.idx[tset] : tset;
-      const uint32_t src = (uint32_t)__cvta_generic_to_shared(sm + (size_t)b * 17);
-      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&tmOut),
-                   "r"(s), "r"(16 * b), "r"(row), "r"(src)
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the unit has read this thread's row
     }
     __syncthreads();  // the next transform's first pass overwrites the grid
   }
@@ -904,35 +879,10 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
               const double2* twL = nullptr;
               FOP_TRY(get_twiddles(h, L, &twL));
               const size_t smem = (size_t)fft_padded_size(L) * sizeof(cd);
-              // FOP_CM_PRUNED=tma: outputs through a TMA tensor store (needs 16-byte aligned rows)
-              CUtensorMap tmOut;
-              std::memset(&tmOut, 0, sizeof tmOut);
-              bool tma_store = pv && !std::strcmp(pv, "tma") && pe.vec2 && logR >= 1;
-              if (tma_store) {
-                // out[row][k][s]: dims {R, L, rows}, strides {R * 8, N * 8} bytes, box {2, 16, 1}
-                typedef CUresult (*EncFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                          const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                          CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-                void* fp = nullptr;
-                cudaDriverEntryPointQueryResult q;
-                if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
-                    q != cudaDriverEntryPointSuccess) {
-                  tma_store = false;
-                } else {
-                  const cuuint64_t dims[3] = {(cuuint64_t)1 << logR, (cuuint64_t)L, (cuuint64_t)P};
-                  const cuuint64_t strides[2] = {((cuuint64_t)8) << logR, (cuuint64_t)N * 8};
-                  const cuuint32_t box[3] = {2, 16, 1}, es[3] = {1, 1, 1};
-                  tma_store = reinterpret_cast<EncFn>(fp)(&tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, ee.out, dims, strides,
-                                                         box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                         CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-                }
-              }
-              auto pk = tma_store ? cm_pruned4096_kernel<true> : cm_pruned4096_kernel<false>;
-              FOP_CUDA(h, cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+              FOP_CUDA(h, cudaFuncSetAttribute(cm_pruned4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
               {
                 ProfScope ps(h, "carr_madan_pruned_kernel");
-                pk<<<std::min(batch, h->sm_count * 16), 256, smem, h->stream>>>(pg, pe, batch, twL, tmOut);
+                cm_pruned4096_kernel<<<std::min(batch, h->sm_count * 16), 256, smem, h->stream>>>(pg, pe, batch, twL);
               }
               FOP_LAUNCH_CHECK(h);
             } else if (logL <= 13) {  // single-CTA transform, length fixed at compile time
