@@ -6,6 +6,7 @@ import sys
 import time
 
 import numpy as np
+import torch  # before the library binds NCCL: torch must load ITS bundled libnccl.so.2
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -42,10 +43,10 @@ def main():
     full = np.concatenate([gathered[r, : calibration.shard_bounds(P, r, world)[1] - calibration.shard_bounds(P, r, world)[0]]
                            for r in range(world)])
     # overlapped form: device buffers, side stream, two alternating buffer pairs
-    import torch
     dev = torch.device(f"cuda:{rank}")
     lt = [torch.tensor(local, device=dev) * (k + 1) for k in range(2)]
     gt = [torch.empty(world * cap, dtype=torch.float64, device=dev) for _ in range(2)]
+    torch.cuda.synchronize(dev)      # the inputs were produced on torch's stream, the gather runs on the handle's
     for k in range(4):
         eng.gather_losses_async(lt[k & 1], gt[k & 1])
     eng.comm_wait()
