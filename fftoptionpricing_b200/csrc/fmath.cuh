@@ -15,8 +15,10 @@
 //     interleaving of N evaluations is written into the source,
 //   * accuracy is <= ~1.5 ulp on the domains the pricers use (tests/test_fmath_host.py measures
 //     it against long double), far inside the 1e-10 parity budget.
-// Polynomials: exp -- Chebyshev-economised fit of (e^r - 1 - r)/r^2 on |r| <= ln2/2 (error 1.4e-18,
-// generated with mpmath, see scripts/gen_fmath_coeffs.py); sin/cos/log/atan -- the classical
+// Polynomials: exp -- Chebyshev fit of (e^r - 1 - r)/r^2 on |r| <= ln2/2 (error 1.4e-18, generated with
+// mpmath; scripts/gen_fmath_coeffs.py regenerates an equivalent degree-10 fit -- same error bound,
+// coefficients equal to 2e-6 relative in the leading term and to rounding in the low ones -- and
+// checks it against this table); sin/cos/log/atan -- the classical
 // minimax sets of Sun's fdlibm (k_sin.c, k_cos.c, e_log.c, s_atan.c; public domain constants).
 // Domains: exp any finite x (clamped to [-746, 710]); sincos |x| < 2^30; log x > 0 normal;
 // atan2 finite.  NaNs propagate; sincos outside its domain returns NaN.
