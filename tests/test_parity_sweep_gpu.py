@@ -269,3 +269,26 @@ def test_fsts_one_step_loop_equals_fsts_price(N, engine, best_oracle):
     ref = best_oracle.fsts(1, 0, prm, N, 7.5, 100.0, .05, .25, steps=1, american=False, payoff=1)
     _, nbad = sweep_report(one, ref, prm, f"FSTS one step N={N}")
     assert nbad == 0
+
+
+@pytest.mark.parametrize("model", ["cgmy", "merton", "vg", "cgmy_cir", "merton_cir_diffusion"])
+def test_c5_grid_sweep_4000_sets_other_model_families_vs_oracle(model, engine, best_oracle):
+    """The bench strike grid and maturities for the other characteristic functions (specialised
+    coefficient kernels per Levy base x time change): 4 000 sets x 8 x 66 each, every price."""
+    P = 4000
+    h = CASES.heston_batch(P, seed=CASES.SEED + 5)[:, 1:]
+    if model == "cgmy":
+        base, tc, prm = 2, 0, CASES.cgmy_batch(P, seed=CASES.SEED + 21)
+    elif model == "merton":
+        base, tc, prm = 1, 0, CASES.merton_batch(P, seed=CASES.SEED + 22)
+    elif model == "vg":
+        base, tc, prm = 3, 0, CASES.vg_batch(P, seed=CASES.SEED + 23)
+    elif model == "cgmy_cir":
+        base, tc, prm = 2, 1, np.hstack([CASES.cgmy_batch(P, seed=CASES.SEED + 24), h])
+    else:
+        base, tc, prm = 1, 2, np.hstack([CASES.merton_batch(P, seed=CASES.SEED + 25), h])
+    K, T = CASES.c5_strikes(), CASES.C5_T
+    got = engine.cos(base, tc, prm, K, 100.0, 0.02, T, 256, 0)
+    ref = best_oracle.cos(base, tc, prm, K, 100.0, 0.02, T, 256, 0)
+    _, nbad = sweep_report(got, ref, prm, f"{model} prices 4000x8x66")
+    assert nbad == 0
