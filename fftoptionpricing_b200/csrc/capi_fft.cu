@@ -68,7 +68,15 @@ struct CmGen {
   double r, T, ada, alpha, discount, b;
   int no_skip;      // FOP_CM_NO_SKIP=1: evaluate every point (A/B runs, tests)
   const int* idx;   // optional: transform p works on parameter set idx[p]
+  // optional: per-set constants already formed by cm_cutoff_kernel (one thread per set, all sets in
+  // parallel) -- otherwise ONE thread of each CTA forms them (tgamma, four pows for CGMY) while the
+  // other 255 wait at the barrier: a third of cm_head_kernel's warp samples (profiles/r2_all_kernels)
+  const CmAux* aux_all = nullptr;
   __device__ void fill(CmAux& me, int p) const {
+    if (aux_all) {
+      me = aux_all[idx ? idx[p] : p];
+      return;
+    }
     make_consts(base, tc, params + (size_t)(idx ? idx[p] : p) * np, me.mc);
     me.c0 = 0.0;
     me.s2t = 0.0;
@@ -136,11 +144,12 @@ struct CmEpi {
 // L <= 8192 fits the single-CTA shared-memory FFT, so the four-step transposition (16 B per point
 // written and re-read) disappears; the head x_j is generated once (cm_head_kernel) and re-read by
 // the R transforms of its set from L2.
-__global__ void cm_cutoff_kernel(CmGen g, int P, int N, int* jc_out) {
+__global__ void cm_cutoff_kernel(CmGen g, int P, int N, int* jc_out, CmAux* aux_out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   CmAux ax;
   g.fill(ax, p);
+  aux_out[p] = ax;
   int jc = N;
   if (ax.s2t > 0.0) {
     const double w2 = fmax((ax.c0 + 750.0) / ax.s2t, 0.0);
@@ -217,6 +226,17 @@ __global__ void __launch_bounds__(256, 2) cm_pruned4096_kernel(PrunedGen pg, Pru
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cd* sm = reinterpret_cast<cd*>(smem_raw);
   const int b = threadIdx.x;
+  // thread-independent twiddles of the generator in shared memory for the whole launch (they were 35
+  // dependent table reads per thread and transform; ncu: a third of the warp samples waited on the
+  // generator's global loads): twA[pair][t] = W_N^{256 t (2 pair)}, twB[t] = W_N^{256 t}, twC[s] = c_s
+  const int npairs = 1 << (pg.logR - 1);
+  cd* twA = sm + fft_padded_size(L);
+  cd* twB = twA + (size_t)npairs * 16;
+  cd* twC = twB + 16;
+  for (int i = b; i < npairs * 16; i += 256) twA[i] = tw_load<-1>(pg.twN, (256 * (i & 15) * 2 * (i >> 4)) & (pg.N - 1));
+  if (b < 16) twB[b] = tw_load<-1>(pg.twN, 256 * b);
+  for (int i = b; i < 2 * npairs; i += 256) twC[i] = tw_load<1>(pg.twN, i * pg.L);
+  __syncthreads();
   const cd w0 = tw_load<-1>(twL, b);               // W_L^{b}: pass 0 (stride 256), q = b
   const cd w1 = tw_load<-1>(twL, (b & 15) * 16);   // W_256^{b mod 16}: pass 1 (stride 16)
   const int base1 = fft_base16(b, 16);
@@ -233,7 +253,8 @@ __global__ void __launch_bounds__(256, 2) cm_pruned4096_kernel(PrunedGen pg, Pru
     const int tset = p >> (logR - 1), s = 2 * (p & ((1 << (logR - 1)) - 1));
     const cd* xs = pg.xbuf + (size_t)tset * L_;
     const cd wbs = tw_load<-1>(pg.twN, (b * s) & (N - 1));
-    const cd cs0 = tw_load<1>(pg.twN, s * L_), cs1 = tw_load<1>(pg.twN, (s + 1) * L_);
+    const cd cs0 = twC[s], cs1 = twC[s + 1];
+    const cd* twAp = twA + (size_t)(s >> 1) * 16;
     cd x[16];
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
@@ -244,8 +265,8 @@ __global__ void __launch_bounds__(256, 2) cm_pruned4096_kernel(PrunedGen pg, Pru
         continue;
       }
       const cd xr = conj(xs[L_ - j]);
-      const cd w1 = wbs * tw_load<-1>(pg.twN, (256 * t * s) & (N - 1));
-      const cd w2 = w1 * (wb * tw_load<-1>(pg.twN, 256 * t));
+      const cd w1 = wbs * twAp[t];
+      const cd w2 = w1 * (wb * twB[t]);
       const cd a = w1 * (xv + cs0 * xr);
       const cd bb = w2 * (xv + cs1 * xr);
       x[t] = mk(0.5 * (a.x - bb.y), 0.5 * (a.y + bb.x));
@@ -772,7 +793,7 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
     const long long tb = std::max<long long>(1, head / (Lmax * 16));
     prune_bytes = Arena::pad((size_t)head) +
                   fft_scratch_bytes((int)Lmax, (int)std::min<long long>(tb * (N / Lmax) / 2 + 1, 1 << 30)) +
-                  2 * Arena::pad((size_t)chunkP * 4);
+                  2 * Arena::pad((size_t)chunkP * 4) + Arena::pad((size_t)chunkP * sizeof(CmAux));
   }
   Arena ar(h);
   FOP_TRY(ar.reserve(stage_bytes(params, (size_t)P * np * 8) +
@@ -798,7 +819,10 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
       int* d_jc = ar.alloc<int>(pc);
       int* d_idx = ar.alloc<int>(pc);
       if (!d_jc || !d_idx) return fail(h, FOP_OOM, "arena exhausted (Carr-Madan routing)");
-      cm_cutoff_kernel<<<(pc + 127) / 128, 128, 0, h->stream>>>(g, pc, N, d_jc);
+      CmAux* d_aux = ar.alloc<CmAux>(pc);
+      if (!d_aux) return fail(h, FOP_OOM, "arena exhausted (Carr-Madan set constants)");
+      cm_cutoff_kernel<<<(pc + 127) / 128, 128, 0, h->stream>>>(g, pc, N, d_jc, d_aux);
+      g.aux_all = d_aux;  // the kernels below load the per-set constants instead of re-forming them
       FOP_LAUNCH_CHECK(h);
       std::vector<int> jc(pc);
       FOP_CUDA(h, cudaMemcpyAsync(jc.data(), d_jc, sizeof(int) * pc, cudaMemcpyDeviceToHost, h->stream));
@@ -878,7 +902,7 @@ int fop_carr_madan(fop_handle_t h, fop_model_t model, const double* params, int 
             if (logL == 12 && !std::getenv("FOP_CM_GENERIC_PRUNED")) {
               const double2* twL = nullptr;
               FOP_TRY(get_twiddles(h, L, &twL));
-              const size_t smem = (size_t)fft_padded_size(L) * sizeof(cd);
+              const size_t smem = ((size_t)fft_padded_size(L) + (size_t)(16 + 2) * (1 << (logR - 1)) + 16) * sizeof(cd);
               FOP_CUDA(h, cudaFuncSetAttribute(cm_pruned4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
               {
                 ProfScope ps(h, "carr_madan_pruned_kernel");
