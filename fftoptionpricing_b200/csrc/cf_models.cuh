@@ -150,11 +150,15 @@ __host__ __device__ __forceinline__ void cf_prepare(int base, int tc, const Mode
   }
   const double s2v = 2.0 * c.adaV * c.adaV;
   const cd kk = kap * kap;
-  const cd delta = csqrt(mk(kk.x + s2v * psi.x, kk.y + s2v * psi.y));
+  const cd delta = csqrt_fast(mk(kk.x + s2v * psi.x, kk.y + s2v * psi.y));
   pre.delta = delta;
   pre.dmk = delta - kap;
-  pre.g = cdiv(pre.dmk, mk(2.0 * delta.x, 2.0 * delta.y));
-  pre.pod = cdiv(psi, delta);
+  // g = (delta - kappa)/(2 delta) and psi/delta share the reciprocal of |delta|^2
+  const double invd = fm_rcp(fma(delta.x, delta.x, delta.y * delta.y));
+  const cd cdl = mk(delta.x * invd, -delta.y * invd);          // 1 / delta
+  const cd gd = pre.dmk * cdl;
+  pre.g = mk(0.5 * gd.x, 0.5 * gd.y);
+  pre.pod = psi * cdl;
 }
 
 // log phi(u) at maturity T, straight-line variants (no data-dependent branch) so that several

@@ -94,6 +94,22 @@ __host__ __device__ __forceinline__ cd csqrt(cd z) {
   const double t = sqrt(0.5 * (r - z.x));
   return mk(fabs(z.y) / (2.0 * t), copysign(t, z.y));
 }
+// the same principal square root without the built-in sqrt / division (two branch-free reciprocal square
+// roots; 1/(2t) is the second one, so there is no division at all) -- the T-independent stage of the
+// coefficient kernels (cf_prepare)
+CX_HD cd csqrt_fast(cd z) {
+  const double ax = fabs(z.x), ay = fabs(z.y);
+  const double n = fma(z.x, z.x, z.y * z.y);
+  const bool zero = !(n > 0.0) && n == 0.0;
+  const double r = fm_sqrt_pos(zero ? 1.0 : n);       // |z|
+  const double tt = 0.5 * (r + ax);                  // > 0
+  double rt;
+  const double t = fm_sqrt_pos(tt, &rt);
+  const double o = (0.5 * ay) * rt;                  // |y| / (2 t)
+  const bool pos = z.x >= 0.0;
+  const double re = pos ? t : o, im = copysign(pos ? o : t, z.y);
+  return mk(zero ? 0.0 : re, zero ? z.y : im);
+}
 // pow(complex, real): polar(exp(y log|z|), y arg z); 0^y = 0 (needed by the reference's own CGMY
 // Carr-Madan test where (M - u) is exactly 0 at omega = 0, test.cpp:841 with alpha + 1 = 2.5 = M).
 // For a positive real base this equals libstdc++'s real pow to rounding.

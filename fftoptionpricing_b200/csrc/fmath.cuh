@@ -167,6 +167,18 @@ FM_HD double fm_rcp_seed(double b) {  // >= 20 correct bits; b normal, nonzero
 #endif
 }
 FM_HD double fm_sqrt(double x) { return sqrt(x); }
+FM_HD double fm_rsqrt_seed(double b) {  // >= 20 correct bits; b normal, positive
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  return r;
+#else
+  // host build (test harness): as coarse as the hardware seed (see fm_rcp_seed)
+  double r = 1.0 / sqrt(b);
+  long long bits; memcpy(&bits, &r, 8); bits &= 0xfffffff800000000ll; memcpy(&r, &bits, 8);
+  return r;
+#endif
+}
 
 template <int N> FM_HD VI<N> fm_hi(VD<N> x) { VI<N> r; FM_LANES r.v[i_] = fm_hi(x.v[i_]); return r; }
 template <int N> FM_HD VI<N> fm_lo(VD<N> x) { VI<N> r; FM_LANES r.v[i_] = fm_lo(x.v[i_]); return r; }
@@ -197,6 +209,23 @@ template <class T> FM_HD T fm_rcp(T b) {
   r = fm_fma(r, e, r);
   return r;
 }
+// 1/sqrt(x) and sqrt(x) for positive normal x, branch-free (no slow-path call as in the built-in sqrt:
+// the CALL / BSSY scaffolding and its register moves cost more issue slots than the arithmetic).
+// Seed 2^-20, two Newton steps (2^-80); sqrt = x * rsqrt with one residual correction (<= 1 ulp).
+FM_HD double fm_rsqrt_pos(double x) {
+  double y = fm_rsqrt_seed(x);
+  const double h = 0.5 * x;
+  y = fma(y, fma(-(h * y), y, 0.5), y);
+  y = fma(y, fma(-(h * y), y, 0.5), y);
+  return y;
+}
+FM_HD double fm_sqrt_pos(double x, double* rsqrt_out = nullptr) {
+  const double y = fm_rsqrt_pos(x);
+  const double s = x * y;
+  if (rsqrt_out) *rsqrt_out = y;
+  return fma(fma(-s, s, x), 0.5 * y, s);
+}
+
 // a / b to <= 1 ulp for normal-range operands.  One Newton step suffices for the reciprocal (seed
 // 2^-20 -> 2^-40): the residual correction of the quotient squares that error again (2^-80).
 template <class T> FM_HD T fm_div(T a, T b) {

@@ -65,6 +65,15 @@ int main() {
     m = fmax(m, ulps(fm_div(a, b), (long double)a / (long double)b));
   }
   printf("div     max ulp %.3f\n", m); if (!(m < 1.01)) ++bad;
+  // sqrt / rsqrt (branch-free, coarse seed)
+  m = 0;
+  double mr = 0;
+  for (int i = 0; i < 2000000; ++i) {
+    double x = exp((U(rng) - 0.5) * 600.0);
+    m = fmax(m, ulps(fm_sqrt_pos(x), sqrtl((long double)x)));
+    mr = fmax(mr, ulps(fm_rsqrt_pos(x), 1.0L / sqrtl((long double)x)));
+  }
+  printf("sqrt    max ulp %.3f\nrsqrt   max ulp %.3f\n", m, mr); if (!(m < 1.01 && mr < 1.5)) ++bad;
   printf(bad ? "FAIL %d\n" : "PASS\n", bad);
   return bad != 0;
 }
