@@ -356,7 +356,16 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
             smem += tabb;
             FOP_CUDA(h, cudaFuncSetAttribute(gt->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           }
-          gt->kern<<<pgrid, 128, smem, h->stream>>>(ga, tmA, tmB);
+          // warp tiles of 16 rows (8 warps per CTA, 16 per SM) measure best: 2.19 vs 2.22 ms on config 5,
+          // 33.9 vs 32.5 TFLOP/s on config 2 (FOP_GEMM_TMA_MB=4 | 1: 32- / 8-row tiles for A/B runs)
+          auto tk = gt->kern2;
+          int tthreads = 256;
+          if (const char* e = std::getenv("FOP_GEMM_TMA_MB")) {
+            if (atoi(e) == 4) { tk = gt->kern; tthreads = 128; }
+            if (atoi(e) == 1 && gt->kern1) { tk = gt->kern1; tthreads = 512; }
+          }
+          FOP_CUDA(h, cudaFuncSetAttribute(tk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          tk<<<pgrid, tthreads, smem, h->stream>>>(ga, tmA, tmB);
         }
         else gemm_kernel<<<ggrid, 32 * (DM_RT / (8 * mb)), gemm_smem, h->stream>>>(ga);
       }

@@ -64,12 +64,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
-template <int NB, int EX = 0>
-__global__ void __launch_bounds__(128, 2)
+template <int NB, int EX = 0, int MB = 4>
+__global__ void __launch_bounds__(32 * (DM_RT / (8 * MB)), 2)
     cos_gemm_tma_kernel(const CosGemmArgs a, const __grid_constant__ CUtensorMap tmA,
                         const __grid_constant__ CUtensorMap tmB) {
   static_assert(EX >= 0 && EX <= 2, "at most two remainder columns fit the tile padding");
-  constexpr int MB = 4;
+  constexpr int NT = 32 * (DM_RT / (8 * MB));
   constexpr int JB = 8 * NB, BS = dm_bs(NB);
   constexpr int STAGE = tm_stage_bytes(NB);
   constexpr uint32_t TX_BYTES = TM_A_BYTES + TM_KC * BS * 8;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128, 2)
     s_strike[tid] = j < a.J ? __ldg(a.strikes + j) : 0.0;
   }
   if (tab) {
-    for (int i = tid; i < a.M * TW; i += 128) {
+    for (int i = tid; i < a.M * TW; i += NT) {
       const int m = i / TW, jj = i - m * TW, j = blk * JB + jj;
       const bool in = j < a.J && jj < JB + EX;
       s_mkt[i] = in ? __ldg(a.mkt + (size_t)m * a.J + j) : 0.0;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128, 2)
     const long long row0 = ((long long)blockIdx.x + t * gridDim.x) * DM_RT;
     const int nrows = (int)min((long long)DM_RT, a.rows - row0);
     __syncthreads();  // the previous tile's epilogue has read the row tables
-    if (tid < nrows) {
+    if (tid < nrows) {   // NT >= 128 = DM_RT
       const int m = (int)((row0 + tid) % a.M);
       s_rowm[tid] = m;
       s_rowscale[tid] = exp(-a.r * __ldg(a.T + m)) * epi.inv;
@@ -294,6 +294,8 @@ __global__ void __launch_bounds__(128, 2)
 struct GemmTmaVariant {
   int NB, EX;
   void (*kern)(const CosGemmArgs, const CUtensorMap, const CUtensorMap);
+  void (*kern2)(const CosGemmArgs, const CUtensorMap, const CUtensorMap);  // 16-row warp tiles (8 warps)
+  void (*kern1)(const CosGemmArgs, const CUtensorMap, const CUtensorMap);  // 8-row warp tiles (16 warps), or null
 };
 const GemmTmaVariant* gemm_tma_variants(int* count);
 
