@@ -301,6 +301,17 @@ def extra_configs(eng, torch, dev, peak, stream):
         eng.profile_enable(False)
         return wall, {k: v[0] / reps for k, v in prof.items()}
 
+    # C1: Black-Scholes Carr-Madan, N = 2^10, ONE parameter set, host in / host out: a latency case
+    # (the reference's own CPU-runnable configuration, test.cpp:619-648)
+    eng.carr_madan(F.GAUSS, 0, [.3], 1024, .25, 1.5, 50.0, .05, 1.0)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        eng.carr_madan(F.GAUSS, 0, [.3], 1024, .25, 1.5, 50.0, .05, 1.0)
+    dt = (time.perf_counter() - t0) / 200
+    out["C1"] = {"workload": "Black-Scholes Carr-Madan 2^10 points x 1 set, host -> host call (latency)",
+                 "ms": dt * 1e3, "value": 1024 / dt, "unit": UNIT,
+                 "roofline": {"bound": "latency", "frac": None,
+                              "what": "one 24 us single-CTA kernel + H2D / D2H / synchronise per call: launch-latency bound by construction"}}
     # C2: Heston COS, 256 u x 1024 strikes, one maturity (batch of 4096 sets)
     P = 4096
     prm = torch.tensor(CASES.heston_batch(P), device=dev)

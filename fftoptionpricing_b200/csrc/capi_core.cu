@@ -133,7 +133,7 @@ int fop_create(fop_handle_t* handle, int device_ordinal) {
   }
   h->sm_count = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
-  h->smem_optin_sm = prop.sharedMemPerMultiprocessor;
+  h->smem_per_sm = prop.sharedMemPerMultiprocessor;
   *handle = h;
   return FOP_OK;
 }

@@ -351,7 +351,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
           // reserved per CTA, ~2.2 KB static)
           size_t smem = cos_tma_smem(g_nb);
           const size_t tabb = cos_tma_tab_bytes(g_nb, M);
-          if (loss && d_mkt && 2 * (smem + tabb + 3400) <= h->smem_optin_sm && !std::getenv("FOP_GEMM_NO_TAB")) {
+          if (loss && d_mkt && 2 * (smem + tabb + 3400) <= h->smem_per_sm && !std::getenv("FOP_GEMM_NO_TAB")) {
             ga.tab_smem = 1;
             smem += tabb;
             FOP_CUDA(h, cudaFuncSetAttribute(gt->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -13,7 +13,7 @@ struct fop_handle_s {
   int device = 0;
   int sm_count = 0;
   size_t smem_optin = 0;
-  size_t smem_optin_sm = 0;  // shared memory per SM
+  size_t smem_per_sm = 0;  // shared memory per SM
   cudaStream_t stream = nullptr;
   std::string err;
   long long launches = 0;

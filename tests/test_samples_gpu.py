@@ -113,3 +113,27 @@ def test_variance_gamma_callable_not_a_builtin_model(engine):
     val = (D[None, :] * np.exp(1j * u[None, :] * (x[:, None] - a))).real.sum(axis=1)
     np.testing.assert_allclose(put, val * np.exp(-r * T) * K, rtol=1e-10, atol=1e-9)
     assert 0 < call[7] < S0      # at-the-money call is a sane number (about 10.98 for these parameters)
+
+
+def test_python_mirror_takes_the_references_callables(engine):
+    """fftoptionpricing_b200.pricing with the reference's own call shapes: lambdas for the
+    characteristic function, the payoff and the asset map (test.cpp:47-79, 342-367, 619-648) against
+    the on-device Black-Scholes model."""
+    from fftoptionpricing_b200 import models, pricing
+    r, sig, T, S0, K, xmax, numX = .05, .3, 1.0, 50.0, 50.0, 5.0, 1024
+
+    def bscf(u):
+        return np.exp(r * T * u + sig * sig * .5 * T * (u * u - u))
+    bs = models.black_scholes(sig)
+    a = pricing.FSTSPrice(numX, xmax, r, T, lambda x: K * np.exp(x), lambda s: max(s - K, 0.0), bscf, engine=engine)
+    b = pricing.FSTSPrice(numX, xmax, r, T, K, 0, bs, engine=engine)
+    lo, hi = int(numX * .3), int(numX * .7)
+    assert np.abs(a - b)[lo:hi].max() < 1e-9
+    a = pricing.CarrMadanCall(numX, .25, S0, r, T, bscf, engine=engine)
+    b = pricing.CarrMadanCall(numX, .25, S0, r, T, bs, engine=engine)
+    assert np.abs(a - b)[lo:hi].max() < 1e-9
+    Ks = [7500, 60, 50, 40, .3]
+    for fn in (pricing.FangOostCallPrice, pricing.FangOostPutPrice, pricing.FangOostCallDelta, pricing.FangOostCallGamma):
+        a = fn(S0, Ks, r, T, 64, bscf, engine=engine)
+        b = fn(S0, Ks, r, T, 64, bs, engine=engine)
+        assert np.abs(a - b)[1:4].max() < 1e-10
