@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "cos_fused_ws.cuh"
+#include "cos_gemm_i8.cuh"
 #include "cos_gemm_tma.cuh"
 #include "cos_gemm_variants.h"
 #include "cos_host_tables.h"
@@ -61,6 +62,20 @@ bool make_tmap_2d(CUtensorMap* m, const double* base, unsigned long long dim0, u
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, es,
              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// digit planes [dim2][dim1][dim0] of bytes (dim0 contiguous), boxes of box2 x box1 x box0, 128-byte swizzle
+bool make_tmap_3d_u8(CUtensorMap* m, const unsigned char* base, unsigned long long dim0, unsigned long long dim1,
+                     unsigned long long dim2, unsigned long long pitch1, unsigned long long pitch2, unsigned box0,
+                     unsigned box1, unsigned box2) {
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {dim0, dim1, dim2};
+  const cuuint64_t strides[2] = {pitch1, pitch2};
+  const cuuint32_t box[3] = {box0, box1, box2};
+  const cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<unsigned char*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 const GemmTmaVariant* pick_gemm_tma(int NB, int EX) {
   if (const char* e = std::getenv("FOP_GEMM_TMA"))
@@ -135,7 +150,14 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const int JB = fused ? 8 * fnb : gx ? 8 * gx->NB : 8 * gv->NB;
   const int Jp = fused ? dm_bs(fnb) : gx ? JB + 2 : nblk * JB;  // row stride of the basis table
   // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
-  const int KK = ((2 * numU + DM_KC - 1) / DM_KC) * DM_KC;
+  const int KK = ((2 * numU + Q8_KC - 1) / Q8_KC) * Q8_KC;  // (a multiple of DM_KC, TM_KC and FW_KC too)
+  // int8 tensor-core contraction (cos_gemm_i8.cuh): call / put prices (and the loss) of a model CF for
+  // up to 80 strikes; everything else, or FOP_GEMM_I8=0, takes the fp64 tensor-core kernels
+  bool use_i8 = !fused && !cf_samples && nk == 1 && kinds[0] <= 1 && J <= Q8_NQ && M <= 128 &&
+                cos_i8_smem(M, J) <= h->smem_optin && tmap_encoder() != nullptr;
+  if (const char* e = std::getenv("FOP_GEMM_I8"))
+    if (e[0] == '0') use_i8 = false;
+  if (std::getenv("FOP_COEFF_GENERIC")) use_i8 = false;  // (the generic coefficient kernel has no quantised output)
 
   // Strike-grid tables (u_k, V_k, strikes, maturities, cos/sin basis): rebuilt only when
   // (K_desc, S0, T, numU) change -- a calibration loop keeps them fixed while theta varies.
@@ -174,7 +196,10 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       uk[k] = du * k;
       vk[k] = vk_put(xMin, uk[k], k) * cp * (k == 0 ? 0.5 : 1.0);
     }
-    const size_t bytes = (tab_doubles + (size_t)KK * Jp) * 8 + 256;
+    double amax = 0.0;
+    for (int k = 0; k < numU; ++k) amax = std::max(amax, std::fabs(vk[k]));
+    cc.amax = amax;
+    const size_t bytes = (tab_doubles + (size_t)KK * Jp + numU) * 8 + 512 + (size_t)Q8_SLICES * Q8_NQ * KK;
     FOP_CUDA(h, cudaStreamSynchronize(h->stream));  // earlier launches may still read the old tables
     if (cc.bytes < bytes) {
       if (cc.dev) cudaFree(cc.dev);
@@ -193,6 +218,21 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
                                                                Jp, cc.dev + boff);
     }
     FOP_LAUNCH_CHECK(h);
+    {  // fixed-point tables of the int8 contraction: vk 2^45 / amax, basis digit planes
+      std::vector<double> vk8(numU);
+      for (int k = 0; k < numU; ++k) vk8[k] = vk[k] > 0.0 ? Q8_A_SCALE : vk[k] < 0.0 ? -Q8_A_SCALE : 0.0;
+      double* d_vk8 = cc.dev + boff + (size_t)KK * Jp;
+      FOP_CUDA(h, cudaMemcpy(d_vk8, vk8.data(), sizeof(double) * numU, cudaMemcpyHostToDevice));
+      unsigned char* d_b8 = reinterpret_cast<unsigned char*>(
+          (reinterpret_cast<uintptr_t>(d_vk8 + numU) + 255) & ~(uintptr_t)255);
+      const int n8 = Q8_NQ * KK;
+      if (J <= Q8_NQ && amax > 0.0) {
+        ProfScope ps(h, "cos_basis_q8_kernel");
+        cos_basis_q8_kernel<<<(n8 + 255) / 256, 256, 0, h->stream>>>(cc.dev + boff, cc.dev + numU, 1.0 / amax, numU,
+                                                                     KK, Jp, J, d_b8);
+      }
+      FOP_LAUNCH_CHECK(h);
+    }
     cc.K = Kh;  cc.T = Th;  cc.S0 = S0;  cc.numU = numU;  cc.JB = JB;  cc.Jp = Jp;  cc.KK = KK;
   }
   const double* d_tab = cc.dev;
@@ -200,6 +240,11 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const double* d_T = cc.dev + 2 * numU + 2 * J;
   const int* d_npow = cc.dt > 0.0 ? reinterpret_cast<const int*>(cc.dev + npow_off) : nullptr;
   const double* d_basis = cc.dev + ((tab_doubles + 1) & ~(size_t)1);
+  const double* d_vk8 = d_basis + (size_t)KK * Jp;
+  const unsigned char* d_b8 = reinterpret_cast<const unsigned char*>(
+      (reinterpret_cast<uintptr_t>(d_vk8 + numU) + 255) & ~(uintptr_t)255);
+  if (cc.amax <= 0.0) use_i8 = false;
+  if (use_i8) nblk = 2;  // two partial row losses per (set, maturity): one per column half
 
   const bool out_host = out && !is_device_ptr(out);
   const bool loss_host = loss && !is_device_ptr(loss);
@@ -223,6 +268,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   need += fused ? Arena::pad((size_t)P * sizeof(ModelConsts)) : Arena::pad((size_t)chunk_rows * KK * 8 * ngreeks);
   if (out_host) need += Arena::pad((size_t)chunk_rows * J * 8);
   if (loss) need += Arena::pad((size_t)P * M * lossblk * 8) + (loss_host ? Arena::pad((size_t)P * 8) : 0);
+  if (use_i8) need += Arena::pad((size_t)chunk_rows);
   FOP_TRY(ar.reserve(need));
 
   const double *d_params = nullptr, *d_mkt = nullptr, *d_w = nullptr;
@@ -237,6 +283,15 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   double* d_out_tmp = out_host ? ar.alloc<double>((size_t)chunk_rows * J) : nullptr;
   double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M * lossblk) : nullptr;
   double* d_loss = loss ? (loss_host ? ar.alloc<double>(P) : loss) : nullptr;
+  unsigned char* d_rowflag = use_i8 ? ar.alloc<unsigned char>((size_t)chunk_rows) : nullptr;
+  CUtensorMap tmB8;
+  if (use_i8) {
+    if (!make_tmap_3d_u8(&tmB8, d_b8, (unsigned long long)KK, Q8_NQ, Q8_SLICES, (unsigned long long)KK,
+                         (unsigned long long)Q8_NQ * KK, Q8_KC, Q8_NQ, Q8_SLICES))
+      return fail(h, FOP_CUDA_ERROR, "tensor map (basis digit planes) could not be encoded");
+    FOP_CUDA(h, cudaFuncSetAttribute(cos_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)cos_i8_smem(M, J)));
+  }
 
   // 32-row warp tiles (4 warps per CTA) measure 1-2 % faster than 16-row tiles (8 warps) for both
   // 66 and 1024 strikes since the epilogue runs from registers; FOP_GEMM_MB=2 selects the latter
@@ -273,6 +328,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ca.r = r;
       ca.params = d_params + (size_t)p0 * np;
       ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = nullptr;
+      ca.C8 = nullptr;  ca.rowflag = nullptr;
       fa.kind = kind;  fa.J = J;  fa.nchunks = KK / FW_KC;  fa.SPT = spt;  fa.depth = 0;
       fa.S0 = S0;
       fa.consts = d_consts + p0;
@@ -308,12 +364,22 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ca.r = r;
       ca.params = d_params + (size_t)p0 * np;
       ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = d_C;
+      ca.C8 = nullptr;  ca.rowflag = nullptr;
+      if (use_i8) {  // digit planes in place of the fp64 matrix (6 of its 8 bytes per entry)
+        ca.C8 = reinterpret_cast<unsigned char*>(d_C);
+        ca.rowflag = d_rowflag;
+        ca.plane = 0;
+        ca.vk = d_vk8;
+        FOP_CUDA(h, cudaMemsetAsync(d_rowflag, 0, (size_t)rows, h->stream));
+      }
       const int ngroups = (pc + ca.spb - 1) / ca.spb;
       const int cgrid = std::min(ngroups, h->sm_count * 32);
       {
         ProfScope ps(h, "cos_coeff_kernel");
         // default: model-specialised kernel (capi_cos_coeff.cu); FOP_COEFF_GENERIC=1: the generic one
-        if (std::getenv("FOP_COEFF_GENERIC") || !cos_coeff_launch_spec(h, ca, 32)) {
+        if (use_i8) {
+          if (!cos_coeff_launch_spec(h, ca, 32)) return fail(h, FOP_INVALID_ARG, "no quantising coefficient kernel");
+        } else if (std::getenv("FOP_COEFF_GENERIC") || !cos_coeff_launch_spec(h, ca, 32)) {
           int ilp = M >= 2 ? 2 : 1;
           if (const char* e = std::getenv("FOP_COEFF_ILP")) ilp = std::max(1, std::min(atoi(e), M >= 2 ? 2 : 1));
           if (ilp >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
@@ -321,6 +387,32 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
         }
       }
       FOP_LAUNCH_CHECK(h);
+    }
+    if (use_i8) {
+      double* out_k = out ? out + (size_t)p0 * M * J : nullptr;
+      CosGemmI8Args qa;
+      qa.kind = kinds[0];  qa.M = M;  qa.J = J;  qa.KK = KK;  qa.rows = rows;  qa.r = r;  qa.S0 = S0;
+      qa.amax = cc.amax;  qa.T = d_T;  qa.strikes = d_K;
+      qa.out = out ? (out_host ? d_out_tmp : out_k) : nullptr;
+      qa.mkt = d_mkt;  qa.w = d_w;
+      qa.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
+      qa.rowflag = d_rowflag;
+      CUtensorMap tmA8;
+      // [rows][6 planes][KK] bytes, addressed as (kk, row, plane)
+      if (!make_tmap_3d_u8(&tmA8, reinterpret_cast<const unsigned char*>(d_C), (unsigned long long)KK,
+                           (unsigned long long)rows, Q8_SLICES, (unsigned long long)Q8_SLICES * KK,
+                           (unsigned long long)KK, Q8_KC, Q8_ROWS, 1))
+        return fail(h, FOP_CUDA_ERROR, "tensor map (coefficient digit planes) could not be encoded");
+      const long long ntiles = (rows + Q8_ROWS - 1) / Q8_ROWS;
+      {
+        ProfScope ps(h, "cos_gemm_kernel");
+        cos_gemm_i8_kernel<<<(unsigned)std::min<long long>(ntiles, h->sm_count), Q8_THREADS, cos_i8_smem(M, J),
+                             h->stream>>>(qa, tmA8, tmB8);
+      }
+      FOP_LAUNCH_CHECK(h);
+      if (out_host)
+        FOP_CUDA(h, cudaMemcpyAsync(out_k, d_out_tmp, (size_t)rows * J * 8, cudaMemcpyDeviceToHost, h->stream));
+      continue;
     }
     for (int ik = 0; ik < nk; ++ik) {
       const int kind = kinds[ik];

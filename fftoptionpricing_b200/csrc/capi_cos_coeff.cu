@@ -15,6 +15,8 @@ bool cos_coeff_launch_spec(fop_handle_t h, const CosCoeffArgs& a_in, int grid_bl
   int shape = 1;  // 128 threads x 5 CTAs/SM: measured best on B200 (profiles/r2_coeff_variants.json)
   if (const char* e = std::getenv("FOP_COEFF_SHAPE")) shape = std::max(0, std::min(atoi(e), kNumCoeffShapes - 1));
   if (a.M < kCoeffShapes[shape].ilp) shape = 1;
+  // quantised output (cos_gemm_i8.cuh); 102: a.Kp == 256 compiled in (GAUSS + CIR on a maturity grid)
+  if (a.C8) shape = shape == 1 ? ((a.Kp == 256 && a.base == BASE_GAUSS && a.tc == TC_CIR && a.npow) ? 102 : 101) : 100;
   const bool grid = a.npow != nullptr, price_only = a.greek_mask == 1;
   int nt = 256;
   CoeffKernel k = nullptr;

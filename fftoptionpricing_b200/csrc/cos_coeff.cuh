@@ -2,6 +2,8 @@
 // cos_coeff_kernel; also compiled for the host by tests/hostemu, which runs the very same source
 // against the oracle on a CPU): characteristic function -> option transform -> times V_k cp.
 #pragma once
+#include <type_traits>
+
 #include "cf_models.cuh"
 
 #ifdef __CUDA_ARCH__
@@ -25,7 +27,73 @@ struct CosCoeffArgs {
   const double* uk;      // [K]
   const double* vk;      // [K]
   double* C;             // [n_greeks][P*M][2 Kp]
+  // quantised output of the int8 tensor-core contraction (cos_gemm_i8.cuh): six signed base-256
+  // digit planes of the fixed-point coefficients, [P*M][6][2 Kp] bytes (the planes of one row are
+  // adjacent: constant offsets from one pointer); a.vk then carries the fixed-point scale.  rowflag[row] is set when a coefficient of the row is not representable
+  // (NaN / overflow): the contraction turns such rows into NaN like the fp64 path would.
+  unsigned char* C8;
+  unsigned char* rowflag;
 };
+
+// ---- fixed-point digit planes (int8 contraction) ---------------------------------------------
+// value q (|q| < 2^47, integer) = sum_s d_s 256^s with SIGNED digits d_s in [-128, 127]: the bytes of
+// (q + BIAS) ^ BIAS with BIAS = 0x808080808080 (adding 128 to every digit makes them the unsigned
+// bytes of q + BIAS).
+constexpr int Q8_SLICES = 6;
+constexpr unsigned long long Q8_BIAS = 0x808080808080ull;
+// x + Q8_MAGIC (one DADD, round to nearest even) leaves (rint(x) + BIAS) mod 2^48 in the low 48 mantissa
+// bits: 2^52 + 2^51 + BIAS is exactly representable and its unit in the last place is 1.
+constexpr double Q8_MAGIC = 6755399441055744.0 + 141289400074368.0;  // 1.5 * 2^52 + 0x808080808080
+// Range test on the high word of x + Q8_MAGIC (1.5 * 2^52 has the high word 0x43380000, BIAS adds
+// 0x8080, the integer its bits 32..47): accepted are (about) |rint(x)| < 2^46 -- twice the nominal
+// range 2^45 of a coefficient; six signed digits reach 0.996 * 2^47.
+constexpr unsigned Q8_HI_LO = 0x43380000u + 0x8080u - 0x4000u;
+__host__ __device__ __forceinline__ bool q8_digits(double x, unsigned& lo, unsigned& hi) {
+  const double t = x + Q8_MAGIC;
+#ifdef __CUDA_ARCH__
+  const unsigned long long b = (unsigned long long)__double_as_longlong(t);
+#else
+  unsigned long long b;
+  __builtin_memcpy(&b, &t, 8);
+#endif
+  const unsigned h = (unsigned)(b >> 32);
+  lo = (unsigned)b ^ 0x80808080u;
+  hi = (h ^ 0x8080u) & 0xffffu;
+  return (h - Q8_HI_LO) < 0x8000u;   // false: NaN or |x| >= 2^46
+}
+// row pointer of the quantised output: the (re, im) byte pair of digit plane 0; plane s lies Kp pairs
+// further, the next maturity row 6 Kp pairs
+struct Q8Row {
+  unsigned short* p;
+};
+__host__ __device__ __forceinline__ void coeff_advance(double2*& c, int n, int Kp) { c += (size_t)n * Kp; }
+__host__ __device__ __forceinline__ void coeff_advance(Q8Row& c, int n, int Kp) { c.p += (size_t)n * Q8_SLICES * Kp; }
+__host__ __device__ __forceinline__ void coeff_store(const CosCoeffArgs&, double2* c, int i, int Kp, double x, double y) {
+  c[(size_t)i * Kp] = make_double2(x, y);
+}
+__host__ __device__ __forceinline__ void coeff_store(const CosCoeffArgs& a, Q8Row c, int i, int Kp, double x, double y) {
+  unsigned short* p = c.p + i * (Q8_SLICES * Kp);
+  const int plane16 = Kp;
+  unsigned xl, xh, yl, yh;
+  const bool okx = q8_digits(x, xl, xh), oky = q8_digits(y, yl, yh);
+  if (!(okx && oky)) {  // NaN or out of range: flag the row, store zeros
+    const size_t off = (size_t)(p - reinterpret_cast<unsigned short*>(a.C8));
+    a.rowflag[off / ((size_t)Q8_SLICES * Kp)] = 1;
+    xl = xh = yl = yh = 0;
+  }
+#ifdef __CUDA_ARCH__
+  p[0] = (unsigned short)__byte_perm(xl, yl, 0x0040);
+  p[plane16] = (unsigned short)__byte_perm(xl, yl, 0x0051);
+  p[2 * plane16] = (unsigned short)__byte_perm(xl, yl, 0x0062);
+  p[3 * plane16] = (unsigned short)__byte_perm(xl, yl, 0x0073);
+  p[4 * plane16] = (unsigned short)__byte_perm(xh, yh, 0x0040);
+  p[5 * plane16] = (unsigned short)__byte_perm(xh, yh, 0x0051);
+#else
+  const unsigned long long ux = xl | ((unsigned long long)xh << 32), uy = yl | ((unsigned long long)yh << 32);
+  for (int s = 0; s < Q8_SLICES; ++s)
+    p[s * plane16] = (unsigned short)(((ux >> (8 * s)) & 0xff) | (((uy >> (8 * s)) & 0xff) << 8));
+#endif
+}
 
 constexpr int COEFF_MAX_SPB = 64;
 
@@ -66,10 +134,10 @@ __host__ __device__ __forceinline__ cd pow_step(PowState& ps, cd E, int d) {
 // loops).  GMASK >= 0: the set of emitted transforms is a compile-time constant (1 = price only).
 // FAST: CIR clock through the re-associated form (cir_logphi_fast) -- specialised kernels; the
 // generic kernel keeps the term-by-term form of the reference (cf_log_cir_given_e).
-template <int MODE, int N, bool GRID, int GMASK = -1, bool FAST = false>
+template <int MODE, int N, bool GRID, int GMASK = -1, bool FAST = false, class CP = double2*>
 __host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, const ModelConsts& mc,
                                             const CfPre& pre, const CirFast& cf, cd E, PowState& ps,
-                                            cd u, double v, double2* crow, int Kp, int m) {
+                                            cd u, double v, CP crow, int Kp, int m) {
   // crow points at maturity m of this (set, u) pair (the caller advances it: no 64-bit row
   // multiplication per store)
   VD<N> Tm;
@@ -101,26 +169,28 @@ __host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, cons
   if (gmask == 1) {  // price only: V_k cp folded into the exponential's scale
     const cx<VD<N>> t = cexp_scaled(lphi, v);
 #pragma unroll
-    for (int i = 0; i < N; ++i) crow[(size_t)i * Kp] = make_double2(t.x.v[i], t.y.v[i]);
+    for (int i = 0; i < N; ++i) coeff_store(a, crow, i, Kp, t.x.v[i], t.y.v[i]);
     return;
   }
-  const cx<VD<N>> d = cexp(lphi);
-  // one CF evaluation feeds every requested transform (price / delta / gamma / theta)
-  double2* cg = crow;
+  if constexpr (std::is_same<CP, double2*>::value) {  // (the quantised output exists for prices only)
+    const cx<VD<N>> d = cexp(lphi);
+    // one CF evaluation feeds every requested transform (price / delta / gamma / theta)
+    double2* cg = crow;
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (!(gmask >> g & 1)) continue;
-    const cx<VD<N>> t = option_transform(g, d, u, a.r);
+    for (int g = 0; g < 4; ++g) {
+      if (!(gmask >> g & 1)) continue;
+      const cx<VD<N>> t = option_transform(g, d, u, a.r);
 #pragma unroll
-    for (int i = 0; i < N; ++i) cg[(size_t)i * Kp] = make_double2(t.x.v[i] * v, t.y.v[i] * v);
-    cg += a.plane / 2;
+      for (int i = 0; i < N; ++i) cg[(size_t)i * Kp] = make_double2(t.x.v[i] * v, t.y.v[i] * v);
+      cg += a.plane / 2;
+    }
   }
 }
 
 // all maturities of one (set, u) pair, ILP at a time
-template <int MODE, int ILP, bool GRID, int GMASK = -1, bool FAST = false>
+template <int MODE, int ILP, bool GRID, int GMASK = -1, bool FAST = false, class CP = double2*>
 __host__ __device__ __forceinline__ void coeff_maturities_g(const CosCoeffArgs& a, const ModelConsts& mc,
-                                                 const CfPre& pre, cd u, double v, double2* crow,
+                                                 const CfPre& pre, cd u, double v, CP crow,
                                                  int Kp) {
   cd E = mk(1.0, 0.0);
   if (MODE == CF_MODE_CIR && GRID) E = cexp(mk(-pre.delta.x * a.dt, -pre.delta.y * a.dt));
@@ -132,9 +202,9 @@ __host__ __device__ __forceinline__ void coeff_maturities_g(const CosCoeffArgs& 
   ps.dprev = 0;
   const int M = a.M;
   int m = 0;
-  for (; m + ILP <= M; m += ILP, crow += (size_t)ILP * Kp)
-    coeff_group<MODE, ILP, GRID, GMASK, FAST>(a, mc, pre, cf, E, ps, u, v, crow, Kp, m);
-  for (; m < M; ++m, crow += Kp) coeff_group<MODE, 1, GRID, GMASK, FAST>(a, mc, pre, cf, E, ps, u, v, crow, Kp, m);
+  for (; m + ILP <= M; m += ILP, coeff_advance(crow, ILP, Kp))
+    coeff_group<MODE, ILP, GRID, GMASK, FAST, CP>(a, mc, pre, cf, E, ps, u, v, crow, Kp, m);
+  for (; m < M; ++m, coeff_advance(crow, 1, Kp)) coeff_group<MODE, 1, GRID, GMASK, FAST, CP>(a, mc, pre, cf, E, ps, u, v, crow, Kp, m);
 }
 template <int MODE, int ILP, int GMASK = -1>
 __host__ __device__ __forceinline__ void coeff_maturities(const CosCoeffArgs& a, const ModelConsts& mc,

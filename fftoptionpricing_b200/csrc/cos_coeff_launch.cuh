@@ -16,6 +16,18 @@ constexpr int kNumCoeffShapes = sizeof(kCoeffShapes) / sizeof(kCoeffShapes[0]);
 
 template <int BASE, int TC, bool GRID, int GMASK>
 CoeffKernel coeff_pick_shape(int shape, int* nt) {
+  // shape >= 100: quantised output (digit planes for the int8 contraction; price only)
+  if constexpr (GMASK == 1) {
+    if (shape >= 100) {
+      if constexpr (BASE == BASE_GAUSS && TC == TC_CIR && GRID) {
+        if (shape == 101) { *nt = 128; return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 128, 5, true, true>; }
+        if (shape == 102) { *nt = 128; return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 128, 5, true, true, 256>; }
+      }
+      *nt = 256;
+      return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 256, 2, true, true>;
+    }
+  }
+  if (shape >= 100) return nullptr;
   if constexpr (BASE == BASE_GAUSS && TC == TC_CIR && GRID && GMASK == 1) {
     if (shape == 1) { *nt = 128; return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 128, 5>; }
     if (shape == 2) { *nt = 128; return cos_coeff_kernel_s<BASE, TC, 4, GRID, GMASK, 128, 3>; }

@@ -30,8 +30,9 @@ struct fop_handle_s {
     double S0 = 0;
     double dt = 0;          // > 0: maturities on the grid T_m = n_m dt (n_m stored after T)
     int numU = 0, Jp = 0, JB = 0, KK = 0;
-    double* dev = nullptr;  // [uk | vk | x | K | T | basis]
+    double* dev = nullptr;  // [uk | vk | x | K | T | basis | vk8 | basis digit planes]
     size_t bytes = 0;
+    double amax = 0;        // max_k |vk|: fixed-point scale of the int8 contraction (cos_gemm_i8.cuh)
   } cos_cache;
   // optional NCCL communicator (capi_comm.cu; opaque here, NCCL is bound at run time)
   void* comm = nullptr;
