@@ -497,6 +497,7 @@ def run_ours(args):
                          prices_out=prices)
         prof = eng.profile_read()
         eng.profile_enable(False)
+        contraction = eng.last_cos_contraction   # (before the extra configurations run other shapes)
         peaks = eng.microbench_fp64() if rank == 0 else None
 
         # ---- N = 1 only: strong-scaling anchor (the fixed 1e6-set sweep on one GPU) + other configs
@@ -573,13 +574,38 @@ def run_ours(args):
         gemm_ach = step_flops / gemm_launches_per_step / gemm_avg_s / 1e12 if gemm_n else None
         coef_ach = (coef_flops * evals_per_step / coef_launches_per_step / coef_avg_s / 1e12
                     if coef_flops and coef_n else None)
-        gemm_entry = {
-            "kernel": "cos_gemm_kernel", "bound": "tensor", "pipe": pipe_note, "achieved": gemm_ach,
-            "peak": peak, "unit": "TFLOP/s", "frac": (gemm_ach / peak) if gemm_ach else None,
-            "traffic": ncu.get("cos_gemm_kernel", {}).get("dram_bytes"),
-            "algorithmic_flops_per_launch": step_flops / gemm_launches_per_step,
-            "algorithmic_bytes_per_launch": rows * (2.0 * NUM_U * 8 + J * 8) / gemm_launches_per_step,
-            "avg_launch_ms": gemm_avg_s * 1e3, "share_of_step": gemm_ms / step_kernel_ms}
+        if contraction == "int8-tcgen05":
+            # int8 digit-plane contraction (cos_gemm_i8.cuh): per launch it streams the 6 coefficient
+            # planes once from HBM (rows x 2 numU x 6 bytes -- the dominant, unavoidable traffic) and
+            # issues 12 N=144 + 2 N=80 tcgen05.mma (M 128, K 32) per 32 kk.  Bound: HBM (0.47 ms of
+            # traffic against 0.43 ms of int8 tensor work at the nominal 4.5 POP/s).
+            hbm = measured_peaks().get("hbm_gbs", 6554.6)
+            alg_bytes = rows * (2.0 * NUM_U * 6 + J * 8 + 2 * 8) / gemm_launches_per_step   # planes in, prices + row losses out
+            i8_ops = rows * 2.0 * NUM_U * 2.0 * (12 * 144 + 2 * 80) / gemm_launches_per_step
+            gemm_entry = {
+                "kernel": "cos_gemm_kernel (cos_gemm_i8_kernel)", "bound": "hbm",
+                "pipe": "tcgen05.mma kind::i8 (exact int8 x int8 -> int32 digit-plane products, accumulators in "
+                        "TMEM) fed by TMA; the kernel streams the coefficient digit planes once",
+                "achieved": alg_bytes / gemm_avg_s / 1e9 if gemm_n else None, "peak": hbm, "unit": "GB/s",
+                "frac": (alg_bytes / gemm_avg_s / 1e9 / hbm) if gemm_n else None,
+                "traffic": ncu.get("cos_gemm_kernel", {}).get("dram_bytes"),
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "int8_tensor": {"ops_per_launch": i8_ops, "achieved_pops": i8_ops / gemm_avg_s / 1e15 if gemm_n else None,
+                                "nominal_peak_pops": 4.5,
+                                "frac_of_nominal": (i8_ops / gemm_avg_s / 1e15 / 4.5) if gemm_n else None},
+                "fp64_equivalent": {"algorithmic_flops_per_launch": step_flops / gemm_launches_per_step,
+                                    "tflops": gemm_ach, "x_fp64_peak": (gemm_ach / peak) if gemm_ach else None,
+                                    "what": "SURVEY 8d flops (4 numU per price) over the launch time: the fp64 "
+                                            "tensor-core kernel this replaces reached 0.835 of the fp64 peak"},
+                "avg_launch_ms": gemm_avg_s * 1e3, "share_of_step": gemm_ms / step_kernel_ms}
+        else:
+            gemm_entry = {
+                "kernel": "cos_gemm_kernel", "bound": "tensor", "pipe": pipe_note, "achieved": gemm_ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": (gemm_ach / peak) if gemm_ach else None,
+                "traffic": ncu.get("cos_gemm_kernel", {}).get("dram_bytes"),
+                "algorithmic_flops_per_launch": step_flops / gemm_launches_per_step,
+                "algorithmic_bytes_per_launch": rows * (2.0 * NUM_U * 8 + J * 8) / gemm_launches_per_step,
+                "avg_launch_ms": gemm_avg_s * 1e3, "share_of_step": gemm_ms / step_kernel_ms}
         coef_entry = {
             "kernel": "cos_coeff_kernel", "bound": "tensor", "pipe": "fp64 pipe (DFMA/DMUL/DADD), dispatch-bound: "
             "an fp64 warp instruction occupies the dispatch port for two cycles (profiles/r2_coeff_variants.json)",
@@ -598,11 +624,16 @@ def run_ours(args):
             "achieved": step_flops / (step_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
             "frac": step_flops / (step_ms * 1e-3) / 1e12 / peak,
             "what": "SURVEY 8d algorithmic flops of the step (4 numU per evaluated price; CF evaluation not "
-                    "counted) over the whole step time"}
+                    "counted) over the whole step time, against the fp64 peak (fp64-equivalent when the "
+                    "contraction runs as exact int8 digit planes on tcgen05)",
+            "contraction": contraction}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if contraction != "int8-tcgen05" else
+                     "f64 (characteristic functions, price map, loss) + exact int8 x int8 -> int32 on 46-bit "
+                     "fixed-point digit planes (contraction)",
             "data": "synthetic", "config": workload_config(P, world),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(prm_host.numel() * 8 + (J + M + 2 * M * J) * 8),

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "fop_get_stream": (C.c_void_p, [C.c_void_p]),
     "fop_synchronize": (C.c_int, [C.c_void_p]),
     "fop_launch_count": (C.c_longlong, [C.c_void_p]),
+    "fop_last_cos_contraction": (C.c_int, [C.c_void_p]),
     "fop_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "fop_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, _dp, C.POINTER(C.c_longlong),
                                    C.c_int, C.POINTER(C.c_int)]),

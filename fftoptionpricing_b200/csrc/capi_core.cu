@@ -158,6 +158,7 @@ int fop_destroy(fop_handle_t h) {
 const char* fop_last_error(fop_handle_t h) { return h ? h->err.c_str() : "null handle"; }
 void* fop_get_stream(fop_handle_t h) { return h ? (void*)h->stream : nullptr; }
 long long fop_launch_count(fop_handle_t h) { return h ? h->launches : 0; }
+int fop_last_cos_contraction(fop_handle_t h) { return h ? h->last_cos_contraction : 0; }
 
 // ---- per-kernel device timing (used by bench.py for the live roofline) ------------------------
 int fop_profile_enable(fop_handle_t h, int enable) {

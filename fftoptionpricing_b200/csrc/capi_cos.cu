@@ -151,10 +151,12 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const int Jp = fused ? dm_bs(fnb) : gx ? JB + 2 : nblk * JB;  // row stride of the basis table
   // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
   const int KK = ((2 * numU + Q8_KC - 1) / Q8_KC) * Q8_KC;  // (a multiple of DM_KC, TM_KC and FW_KC too)
-  // int8 tensor-core contraction (cos_gemm_i8.cuh): call / put prices (and the loss) of a model CF for
-  // up to 80 strikes; everything else, or FOP_GEMM_I8=0, takes the fp64 tensor-core kernels
-  bool use_i8 = !fused && !cf_samples && nk == 1 && kinds[0] <= 1 && J <= Q8_NQ && M <= 128 &&
-                cos_i8_smem(M, J) <= h->smem_optin && tmap_encoder() != nullptr;
+  // int8 tensor-core contraction (cos_gemm_i8.cuh): call / put prices (and the loss) of a model CF with
+  // up to 16 maturities (market tables of a strike block in shared memory); everything else, or
+  // FOP_GEMM_I8=0, takes the fp64 tensor-core kernels
+  const int nblk8 = (J + Q8_NQ - 1) / Q8_NQ, J8 = nblk8 * Q8_NQ;
+  bool use_i8 = !fused && !cf_samples && nk == 1 && kinds[0] <= 1 && cos_i8_smem(M) + 512 <= h->smem_optin &&
+                tmap_encoder() != nullptr;
   if (const char* e = std::getenv("FOP_GEMM_I8"))
     if (e[0] == '0') use_i8 = false;
   if (std::getenv("FOP_COEFF_GENERIC")) use_i8 = false;  // (the generic coefficient kernel has no quantised output)
@@ -199,7 +201,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     double amax = 0.0;
     for (int k = 0; k < numU; ++k) amax = std::max(amax, std::fabs(vk[k]));
     cc.amax = amax;
-    const size_t bytes = (tab_doubles + (size_t)KK * Jp + numU) * 8 + 512 + (size_t)Q8_SLICES * Q8_NQ * KK;
+    const size_t bytes = (tab_doubles + (size_t)KK * Jp + numU) * 8 + 512 + (size_t)Q8_SLICES * J8 * KK;
     FOP_CUDA(h, cudaStreamSynchronize(h->stream));  // earlier launches may still read the old tables
     if (cc.bytes < bytes) {
       if (cc.dev) cudaFree(cc.dev);
@@ -225,11 +227,11 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       FOP_CUDA(h, cudaMemcpy(d_vk8, vk8.data(), sizeof(double) * numU, cudaMemcpyHostToDevice));
       unsigned char* d_b8 = reinterpret_cast<unsigned char*>(
           (reinterpret_cast<uintptr_t>(d_vk8 + numU) + 255) & ~(uintptr_t)255);
-      const int n8 = Q8_NQ * KK;
-      if (J <= Q8_NQ && amax > 0.0) {
+      const long long n8 = (long long)J8 * KK;
+      if (amax > 0.0) {
         ProfScope ps(h, "cos_basis_q8_kernel");
-        cos_basis_q8_kernel<<<(n8 + 255) / 256, 256, 0, h->stream>>>(cc.dev + boff, cc.dev + numU, 1.0 / amax, numU,
-                                                                     KK, Jp, J, d_b8);
+        cos_basis_q8_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, h->stream>>>(cc.dev + boff, cc.dev + numU,
+                                                                                 1.0 / amax, numU, KK, Jp, J, J8, d_b8);
       }
       FOP_LAUNCH_CHECK(h);
     }
@@ -244,7 +246,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const unsigned char* d_b8 = reinterpret_cast<const unsigned char*>(
       (reinterpret_cast<uintptr_t>(d_vk8 + numU) + 255) & ~(uintptr_t)255);
   if (cc.amax <= 0.0) use_i8 = false;
-  if (use_i8) nblk = 2;  // two partial row losses per (set, maturity): one per column half
+  if (use_i8) nblk = 2 * nblk8;  // two partial row losses per (set, maturity, strike block): one per column half
 
   const bool out_host = out && !is_device_ptr(out);
   const bool loss_host = loss && !is_device_ptr(loss);
@@ -286,11 +288,11 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   unsigned char* d_rowflag = use_i8 ? ar.alloc<unsigned char>((size_t)chunk_rows) : nullptr;
   CUtensorMap tmB8;
   if (use_i8) {
-    if (!make_tmap_3d_u8(&tmB8, d_b8, (unsigned long long)KK, Q8_NQ, Q8_SLICES, (unsigned long long)KK,
-                         (unsigned long long)Q8_NQ * KK, Q8_KC, Q8_NQ, Q8_SLICES))
+    if (!make_tmap_3d_u8(&tmB8, d_b8, (unsigned long long)KK, (unsigned long long)J8, Q8_SLICES,
+                         (unsigned long long)KK, (unsigned long long)J8 * KK, Q8_KC, Q8_NQ, Q8_SLICES))
       return fail(h, FOP_CUDA_ERROR, "tensor map (basis digit planes) could not be encoded");
     FOP_CUDA(h, cudaFuncSetAttribute(cos_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)cos_i8_smem(M, J)));
+                                     (int)cos_i8_smem(M)));
   }
 
   // 32-row warp tiles (4 warps per CTA) measure 1-2 % faster than 16-row tiles (8 warps) for both
@@ -314,6 +316,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       FOP_CUDA(h, cudaFuncSetAttribute(gt->kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cos_tma_smem(g_nb)));
   }
 
+  h->last_cos_contraction = fused ? 3 : use_i8 ? 2 : 1;
   for (long long p0 = 0; p0 < P; p0 += chunkP) {
     const int pc = (int)std::min<long long>(chunkP, P - p0);
     const long long rows = (long long)pc * M;
@@ -391,7 +394,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     if (use_i8) {
       double* out_k = out ? out + (size_t)p0 * M * J : nullptr;
       CosGemmI8Args qa;
-      qa.kind = kinds[0];  qa.M = M;  qa.J = J;  qa.KK = KK;  qa.rows = rows;  qa.r = r;  qa.S0 = S0;
+      qa.kind = kinds[0];  qa.M = M;  qa.J = J;  qa.KK = KK;  qa.nblk = nblk8;  qa.rows = rows;  qa.r = r;  qa.S0 = S0;
       qa.amax = cc.amax;  qa.T = d_T;  qa.strikes = d_K;
       qa.out = out ? (out_host ? d_out_tmp : out_k) : nullptr;
       qa.mkt = d_mkt;  qa.w = d_w;
@@ -406,8 +409,9 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       const long long ntiles = (rows + Q8_ROWS - 1) / Q8_ROWS;
       {
         ProfScope ps(h, "cos_gemm_kernel");
-        cos_gemm_i8_kernel<<<(unsigned)std::min<long long>(ntiles, h->sm_count), Q8_THREADS, cos_i8_smem(M, J),
-                             h->stream>>>(qa, tmA8, tmB8);
+        // persistent, one CTA per SM: the SMs are divided among the strike blocks
+        const dim3 qgrid((unsigned)std::min<long long>(ntiles, std::max(1, h->sm_count / nblk8)), (unsigned)nblk8);
+        cos_gemm_i8_kernel<<<qgrid, Q8_THREADS, cos_i8_smem(M), h->stream>>>(qa, tmA8, tmB8);
       }
       FOP_LAUNCH_CHECK(h);
       if (out_host)

@@ -36,6 +36,7 @@
 //             behind plane 5 and adding zeros to the first eight columns of the next level.  Thirteen
 //             instructions per 32 kk instead of 26.  tcgen05.commit releases the stage / publishes
 //             the accumulators.
+//   (more than 72 strikes: blockIdx.y walks blocks of 72 columns, each a pass over the coefficient planes)
 //   warps 2-9 epilogue (a warp reads TMEM lanes 32 (warp % 4) .. +31; two warps share a lane quarter
 //             and take 36 columns each): tcgen05.ld the seven level accumulators, write zeros back
 //             (tcgen05.st: every MMA accumulates, no first-instruction special case), recombine in
@@ -71,6 +72,7 @@ constexpr double Q8_B_SCALE = 70368744177664.0;    // 2^46
 struct CosGemmI8Args {
   int kind;
   int M, J, KK;
+  int nblk;                     // strike blocks of 72 columns (blockIdx.y)
   long long rows;
   double r, S0;
   double amax;                  // val = amax 2^-91 sum qa qb
@@ -79,27 +81,28 @@ struct CosGemmI8Args {
   double* out;                  // [rows][J] or nullptr
   const double* mkt;            // [M][J] or nullptr
   const double* w;              // [M][J] or nullptr
-  double* rowloss;              // [rows][2] (one partial sum per column half) or nullptr
+  double* rowloss;              // [rows][nblk][2] (one partial sum per block and column half) or nullptr
   const unsigned char* rowflag; // [rows]: row holds a non-representable coefficient -> NaN
 };
-__host__ inline size_t cos_i8_smem(int M, int J) {
-  return (size_t)Q8_RING + 1024 + ((size_t)2 * M * J + Q8_NQ + M) * 8;
+// ring + alignment slack + market / weight tables of one strike block [2][M][72] + strikes + discounts
+__host__ inline size_t cos_i8_smem(int M) {
+  return (size_t)Q8_RING + 1024 + ((size_t)2 * M * Q8_NQ + Q8_NQ + M) * 8;
 }
 
-// basis digit planes B8[6][72][KK] (K-major: one row of KK bytes per strike) from basis[KK][Jp],
-// row kk weighted by |V_k cp| / amax (see the scaling note above)
+// basis digit planes B8[6][J8][KK] (K-major: one row of KK bytes per strike; J8 = strike count padded
+// to whole 72-column blocks) from basis[KK][Jp], row kk weighted by |V_k cp| / amax (scaling note above)
 static __global__ void cos_basis_q8_kernel(const double* __restrict__ basis, const double* __restrict__ vk,
-                                           double inv_amax, int numU, int KK, int Jp, int J,
+                                           double inv_amax, int numU, int KK, int Jp, int J, int J8,
                                            unsigned char* __restrict__ B8) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= Q8_NQ * KK) return;
+  if (idx >= J8 * KK) return;
   const int j = idx / KK, kk = idx - j * KK;
   const double v = (j < J && kk < 2 * numU) ? basis[(size_t)kk * Jp + j] * (fabs(vk[kk >> 1]) * inv_amax) : 0.0;
   unsigned lo, hi;
   q8_digits(v * Q8_B_SCALE, lo, hi);   // |v| <= 1: always representable
   const unsigned long long u = lo | ((unsigned long long)hi << 32);
 #pragma unroll
-  for (int s = 0; s < Q8_SLICES; ++s) B8[((size_t)s * Q8_NQ + j) * KK + kk] = (unsigned char)(u >> (8 * s));
+  for (int s = 0; s < Q8_SLICES; ++s) B8[((size_t)s * J8 + j) * KK + kk] = (unsigned char)(u >> (8 * s));
 }
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
@@ -197,9 +200,12 @@ static __global__ void __launch_bounds__(Q8_THREADS, 1)
   unsigned char* ring = smem_dyn + ((1024u - (tm_smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* ringB = ring + (size_t)Q8_A_BYTES;
   double* s_mkt = reinterpret_cast<double*>(ring + (size_t)Q8_RING);
-  double* s_w = s_mkt + (size_t)a.M * a.J;
-  double* s_strike = s_w + (size_t)a.M * a.J;
+  double* s_w = s_mkt + (size_t)a.M * Q8_NQ;
+  double* s_strike = s_w + (size_t)a.M * Q8_NQ;
   double* s_rs = s_strike + Q8_NQ;
+  const int blk = blockIdx.y;
+  const int jbase = blk * Q8_NQ;
+  const int jvalid = min(Q8_NQ, a.J - jbase);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nch = a.KK / Q8_KC;
@@ -229,11 +235,13 @@ static __global__ void __launch_bounds__(Q8_THREADS, 1)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < a.M * a.J; i += Q8_THREADS) {
-    s_mkt[i] = a.mkt ? __ldg(a.mkt + i) : 0.0;
-    s_w[i] = a.w ? __ldg(a.w + i) : 1.0;
+  for (int i = tid; i < a.M * Q8_NQ; i += Q8_THREADS) {
+    const int m = i / Q8_NQ, jj = i - m * Q8_NQ;
+    const bool in = jj < jvalid;
+    s_mkt[i] = (in && a.mkt) ? __ldg(a.mkt + (size_t)m * a.J + jbase + jj) : 0.0;
+    s_w[i] = in ? (a.w ? __ldg(a.w + (size_t)m * a.J + jbase + jj) : 1.0) : 0.0;
   }
-  if (tid < Q8_NQ) s_strike[tid] = tid < a.J ? __ldg(a.strikes + tid) : 0.0;
+  if (tid < Q8_NQ) s_strike[tid] = tid < jvalid ? __ldg(a.strikes + jbase + tid) : 0.0;
   if (tid < a.M) s_rs[tid] = exp(-a.r * __ldg(a.T + tid)) * epi.inv;
   // the eight zero rows behind basis plane 5 of every stage (read by the N = 80 instructions)
   for (int i = tid; i < Q8_STB * (Q8_B_PAD / 4); i += Q8_THREADS) {
@@ -259,7 +267,7 @@ static __global__ void __launch_bounds__(Q8_THREADS, 1)
         const long long r0 = ((long long)blockIdx.x + t * gridDim.x) * Q8_ROWS;
         if (gch >= Q8_STB) q8_wait(&s_emptyB[sB], (uint32_t)(((gch / Q8_STB) - 1) & 1));
         tm_mbar_expect_tx(&s_fullB[sB], Q8_B_BYTES);
-        tma_load_3d(ringB + (size_t)sB * Q8_B_STAGE, &tmB, ch * Q8_KC, 0, 0, &s_fullB[sB]);
+        tma_load_3d(ringB + (size_t)sB * Q8_B_STAGE, &tmB, ch * Q8_KC, jbase, 0, &s_fullB[sB]);
 #pragma unroll 1
         for (int i = 0; i < Q8_SLICES; ++i) {
           if (gch >= 1) q8_wait(&s_emptyA[i], (uint32_t)((gch - 1) & 1));
@@ -334,9 +342,9 @@ static __global__ void __launch_bounds__(Q8_THREADS, 1)
       const int m = valid ? (int)(row % a.M) : 0;
       const double rs = s_rs[m];
       const bool bad = valid && a.rowflag && a.rowflag[row] != 0;
-      double* orow = a.out && valid ? a.out + (size_t)row * a.J : nullptr;
-      const double* mrow = s_mkt + (size_t)m * a.J;
-      const double* wrow = s_w + (size_t)m * a.J;
+      double* orow = a.out && valid ? a.out + (size_t)row * a.J + jbase : nullptr;
+      const double* mrow = s_mkt + (size_t)m * Q8_NQ;
+      const double* wrow = s_w + (size_t)m * Q8_NQ;
       double lsum = 0.0;
       q8_wait(&s_tfull, (uint32_t)(t & 1));
       tc_fence_after();
@@ -363,7 +371,7 @@ static __global__ void __launch_bounds__(Q8_THREADS, 1)
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           const int j = j0 + e;
-          if (e < width && j < a.J) {
+          if (e < width && j < jvalid) {
             // sum_L S_L 256^L in two halves: levels 0..3 (< 2^50) and 4..6 (< 2^42)
             // (wide multiply-adds on top of the conversion constant: seven integer instructions)
             long long lo = 0x4338000000000000ll, hi = 0x4338000000000000ll;
@@ -390,7 +398,7 @@ static __global__ void __launch_bounds__(Q8_THREADS, 1)
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       tm_mbar_arrive(&s_tempty);  // every epilogue thread has read and re-zeroed its accumulators
-      if (a.rowloss && valid) a.rowloss[row * 2 + half] = lsum;
+      if (a.rowloss && valid) a.rowloss[(row * a.nblk + blk) * 2 + half] = lsum;
     }
   }
   tc_fence_before();

@@ -17,6 +17,7 @@ struct fop_handle_s {
   cudaStream_t stream = nullptr;
   std::string err;
   long long launches = 0;
+  int last_cos_contraction = 0;  // fop_last_cos_contraction
   // bump arena for per-call device temporaries (grown on demand, reused across calls)
   unsigned char* arena = nullptr;
   size_t arena_cap = 0, arena_used = 0;

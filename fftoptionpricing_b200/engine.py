@@ -111,6 +111,11 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._L.fop_launch_count(self._h))
 
+    @property
+    def last_cos_contraction(self) -> str:
+        """Contraction kernel of the last COS call: 'fp64-dmma', 'int8-tcgen05', 'fused' or 'none'."""
+        return ("none", "fp64-dmma", "int8-tcgen05", "fused")[int(self._L.fop_last_cos_contraction(self._h))]
+
     def profile_enable(self, on: bool = True):
         """Bracket every kernel launch with CUDA events on the handle's stream."""
         self._check(self._L.fop_profile_enable(self._h, int(bool(on))))

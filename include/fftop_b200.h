@@ -105,6 +105,10 @@ void* fop_get_stream(fop_handle_t handle);       /* the handle's cudaStream_t */
 int fop_synchronize(fop_handle_t handle);
 /* number of this library's kernel launches since fop_create (for bench.py's gpu_launches) */
 long long fop_launch_count(fop_handle_t handle);
+/* contraction kernel the last fop_cos* call on this handle used (for benchmarks / tests):
+ * 0 none yet, 1 fp64 tensor cores (mma.sync DMMA), 2 int8 digit planes on tcgen05 / TMEM
+ * (call / put prices of up to 72 strikes; FOP_GEMM_I8=0 disables it), 3 fused single kernel */
+int fop_last_cos_contraction(fop_handle_t handle);
 
 /* Optional per-kernel device timing: while enabled every kernel launch of this library is
  * bracketed by CUDA events on the handle's stream.  fop_profile_read synchronises, writes the

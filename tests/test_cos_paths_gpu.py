@@ -1,6 +1,8 @@
 """GPU parity tests of the two COS execution paths and of the maturity-grid shortcut.
 
-* split path (default): cos_coeff_kernel + cos_gemm_dmma_kernel;
+* split path (default): cos_coeff_kernel + contraction -- every test of this file runs with BOTH
+  contractions: the int8 digit-plane kernel on tcgen05 (default for call / put prices of up to 72
+  strikes, cos_gemm_i8.cuh) and the fp64 tensor-core kernels (FOP_GEMM_I8=0);
 * fused path (FOP_COS_PATH=fused): cos_fused_ws_kernel, warp-specialised producers/consumers;
 * maturities on a common grid T_m = n_m dt use exp(-delta T_m) = exp(-delta dt)^{n_m}; off-grid
   maturities take one exp per maturity.
@@ -26,6 +28,15 @@ def engine():
     eng = F.Engine(0)
     yield eng
     eng.close()
+
+
+@pytest.fixture(autouse=True, params=["i8", "f64"])
+def contraction(request, monkeypatch):
+    if request.param == "f64":
+        monkeypatch.setenv("FOP_GEMM_I8", "0")
+    else:
+        monkeypatch.delenv("FOP_GEMM_I8", raising=False)
+    return request.param
 
 
 def _strikes(J, S0=100.0):
