@@ -397,6 +397,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       qa.kind = kinds[0];  qa.M = M;  qa.J = J;  qa.KK = KK;  qa.nblk = nblk8;  qa.rows = rows;  qa.r = r;  qa.S0 = S0;
       qa.amax = cc.amax;  qa.T = d_T;  qa.strikes = d_K;
       qa.out = out ? (out_host ? d_out_tmp : out_k) : nullptr;
+      qa.vec2 = (J % 2 == 0) && (reinterpret_cast<uintptr_t>(qa.out) % 16 == 0);
       qa.mkt = d_mkt;  qa.w = d_w;
       qa.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
       qa.rowflag = d_rowflag;
