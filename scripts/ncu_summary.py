@@ -18,7 +18,14 @@ KEEP = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
-        'smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio']
+        'smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio',
+        # tensor pipe (tcgen05): share of the launch the pipe is active, int8 sub-pipe cycles, TMEM traffic
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+        'TPC.TriageCompute.sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg',
+        'smsp__sass_inst_executed_op_tmem_ldt.sum', 'smsp__sass_inst_executed_op_tmem_stt.sum',
+        'l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed']
 
 
 def summarise(rep):
