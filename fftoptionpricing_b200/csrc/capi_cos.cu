@@ -152,10 +152,11 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
   const int KK = ((2 * numU + Q8_KC - 1) / Q8_KC) * Q8_KC;  // (a multiple of DM_KC, TM_KC and FW_KC too)
   // int8 tensor-core contraction (cos_gemm_i8.cuh): call / put prices (and the loss) of a model CF with
-  // up to 16 maturities (market tables of a strike block in shared memory); everything else, or
+  // up to 16 maturities (market tables of a strike block in shared memory) and numU <= 8192 (int32
+  // accumulators cannot overflow); everything else, or
   // FOP_GEMM_I8=0, takes the fp64 tensor-core kernels
   const int nblk8 = (J + Q8_NQ - 1) / Q8_NQ, J8 = nblk8 * Q8_NQ;
-  bool use_i8 = !fused && !cf_samples && nk == 1 && kinds[0] <= 1 && cos_i8_smem(M) + 512 <= h->smem_optin &&
+  bool use_i8 = !fused && !cf_samples && nk == 1 && kinds[0] <= 1 && cos_i8_smem(M) + 512 <= h->smem_optin && KK <= 16384 &&
                 tmap_encoder() != nullptr;
   if (const char* e = std::getenv("FOP_GEMM_I8"))
     if (e[0] == '0') use_i8 = false;

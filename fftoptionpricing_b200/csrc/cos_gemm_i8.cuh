@@ -11,8 +11,9 @@
 //   Bas'[kk][j] = Bas[kk][j] |V_k cp| / amax    = qb 2^-46,   qb integer, |qb| <= 2^46   (once per strike grid)
 //   val = amax sum_kk C' Bas',   amax = max_k |V_k cp|
 // Each integer is split into six signed base-256 digits (int8): q = sum_s d_s 256^s.  The product of
-// two digit planes is an EXACT int8 x int8 -> int32 tensor-core GEMM (products <= 2^14, 512 terms and
-// at most six plane pairs per accumulator: < 2^26), and
+// two digit planes is an EXACT int8 x int8 -> int32 tensor-core GEMM (products <= 2^14, at most six
+// plane pairs per accumulator: < 2^26 for the usual 512 terms, and below 2^31 for any digits up to
+// 16 384 terms = numU 8 192, the limit the host enforces), and
 //   qa qb = sum_{s,t} a_s b_t 256^{s+t}.
 // The 26 plane pairs with s + t >= 4 are kept, accumulated per level L = s + t - 4 = 0..6 in its own
 // TMEM columns; the 10 pairs below contribute < 2^-53 of full scale per term.  What remains is the
@@ -334,9 +335,10 @@ static __global__ void __launch_bounds__(Q8_THREADS, 1)
     const int half = (warp - 2) >> 2;       // column half: columns 36 half .. 36 half + 35
     const int rr = q * 32 + lane;
     const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + half * 36;
-    // val = amax 2^-91 sum_L S_L 256^(L + 4) = amax (lo 2^-59 + hi 2^-27)
+    // val = amax 2^-91 sum_L S_L 256^(L + 4) = amax (lo 2^-59 + mid 2^-35 + top 2^-11)
     const double c_lo = a.amax * 0x1p-59;
-    const double c_hi = a.amax * 0x1p-27;
+    const double c_mid = a.amax * 0x1p-35;
+    const double c_top = a.amax * 0x1p-11;
     // zero the accumulators once (every MMA accumulates)
 #pragma unroll
     for (int L = 0; L < Q8_LEVELS; ++L) {
@@ -385,19 +387,21 @@ static __global__ void __launch_bounds__(Q8_THREADS, 1)
         }
 #pragma unroll
         for (int e = 0; e < (cb < 4 ? 8 : 4); ++e) {
-          // sum_L S_L 256^L in two halves: levels 0..3 (< 2^50) and 4..6 (< 2^42); wide multiply-adds
-          // on top of the conversion constant: seven integer instructions, then exact DADDs
-          long long lo = 0x4338000000000000ll, hi = 0x4338000000000000ll;
-          lo += (long long)S[3][e] * 16777216;
+          // sum_L S_L 256^L in three groups (levels 0..2, 3..5, 6) that stay below 2^48 for ANY int32
+          // accumulators, so the integer -> double conversion by the 1.5 * 2^52 constant is exact; the
+          // wide multiply-adds start from that constant: six integer instructions, three exact DADDs
+          long long lo = 0x4338000000000000ll, mid = 0x4338000000000000ll, top = 0x4338000000000000ll;
           lo += (long long)S[2][e] * 65536;
           lo += (long long)S[1][e] * 256;
           lo += (long long)S[0][e];
-          hi += (long long)S[6][e] * 65536;
-          hi += (long long)S[5][e] * 256;
-          hi += (long long)S[4][e];
+          mid += (long long)S[5][e] * 65536;
+          mid += (long long)S[4][e] * 256;
+          mid += (long long)S[3][e];
+          top += (long long)S[6][e];
           const double dlo = __longlong_as_double(lo) - 6755399441055744.0;
-          const double dhi = __longlong_as_double(hi) - 6755399441055744.0;
-          vals[cb * 8 + e] = fma(dhi, c_hi, dlo * c_lo);
+          const double dmid = __longlong_as_double(mid) - 6755399441055744.0;
+          const double dtop = __longlong_as_double(top) - 6755399441055744.0;
+          vals[cb * 8 + e] = fma(dtop, c_top, fma(dmid, c_mid, dlo * c_lo));
         }
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

@@ -22,6 +22,9 @@ from ncu_summary import opcode_mix, summarise  # noqa: E402
 
 FP64_PEAK_TFLOPS = 37.0   # DMMA probe of fop_microbench_fp64 on B200 (bench.py re-measures it live)
 HBM_PEAK_GBS = 6554.6     # MEASURED_PEAKS.json
+INT8_PEAK_POPS = 4.5      # nominal dense int8 tensor rate of B200 (no measured entry)
+PROF_NAME = {"c5i8": "c5", "c2i8": "c2"}            # workload of scripts/prof_workloads.py
+ENV = {"c5": {"FOP_GEMM_I8": "0"}, "c2": {"FOP_GEMM_I8": "0"}}
 
 # workload -> (kernel regex, max launches, {kernel substring: (bound, algorithmic amount, what)})
 W = {
@@ -32,6 +35,17 @@ W = {
     "c2": ("cos_coeff|cos_gemm", 2, {
         "cos_coeff": ("fp64", None, "CF evaluation: executed fp64 flops"),
         "cos_gemm": ("fp64", 2048 * 1024 * 4.0 * 256, "4 numU flops per price")}),
+    # the default contraction of call / put prices: int8 digit planes on tcgen05 (cos_gemm_i8.cuh); the
+    # workloads "c5" / "c2" above run with FOP_GEMM_I8=0 (fp64 tensor-core kernels)
+    "c5i8": ("cos_coeff|cos_gemm|cos_loss_finalize", 3, {
+        "cos_coeff": ("fp64", None, "CF evaluation + digit-plane output: executed fp64 flops (SURVEY 8d assigns none)"),
+        "cos_gemm_i8": ("hbm", 16384 * 8 * (512 * 6.0 + 66 * 8.0 + 16.0),
+                        "6 B per coefficient digit planes read once + 8 B per price + 16 B row loss written"),
+        "cos_loss_finalize": ("hbm", 16384 * 8 * 16.0 + 16384 * 8.0, "row losses read + set losses written")}),
+    "c2i8": ("cos_coeff|cos_gemm", 2, {
+        "cos_coeff": ("fp64", None, "CF evaluation + digit-plane output: executed fp64 flops"),
+        "cos_gemm_i8": ("int8", 2048 * 512 * 2.0 * (12 * 144 + 2 * 80) * 15,
+                        "int8 tensor ops issued: 12 N=144 + 2 N=80 tcgen05.mma (M 128, K 32) per 32 kk, 15 strike blocks")}),
     "c3pair": ("fsts_pair", 1, {"fsts_pair": ("fp64", 592 * 256 * (2 * 5 * 4096 * 12 + 8 * 4096.0),
                                               "steps x (2 x 5 N log2 N + 8 N) flops per set")}),
     "c3single": ("fsts_kernel", 1, {"fsts_kernel": ("fp64", 592 * 256 * (2 * 5 * 4096 * 12 + 8 * 4096.0),
@@ -69,6 +83,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "r2_all_kernels_ncu.json"),
                     help="summary JSON (gpurun_out/ is what travels back from the GPU box; copy it to profiles/)")
     ap.add_argument("--keep", action="store_true", help="keep the .ncu-rep files (large)")
+    ap.add_argument("--merge", default="", help="existing summary whose other workloads are carried over")
     args = ap.parse_args()
     names = [n for n in (args.only.split(",") if args.only else W)]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -77,14 +92,16 @@ def main():
         rx, cnt, table = W[nm]
         rep = os.path.join(ROOT, "gpurun_out", f"r2_all_{nm}")
         # the workload first runs once without ncu (profiling recipe: capture only what exited 0)
-        r0 = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "prof_workloads.py"), nm],
-                            capture_output=True, text=True)
+        pn = PROF_NAME.get(nm, nm)
+        env = dict(os.environ, **ENV.get(nm, {}))
+        r0 = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "prof_workloads.py"), pn],
+                            capture_output=True, text=True, env=env)
         if r0.returncode != 0:
             result.append({"workload": nm, "error": r0.stderr[-500:]})
             continue
         cmd = ["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", f"regex:{rx}",
-               "-c", str(cnt), "-f", "-o", rep, sys.executable, os.path.join(ROOT, "scripts", "prof_workloads.py"), nm]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+               "-c", str(cnt), "-f", "-o", rep, sys.executable, os.path.join(ROOT, "scripts", "prof_workloads.py"), pn]
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0 or not os.path.exists(rep + ".ncu-rep"):
             result.append({"workload": nm, "error": (r.stdout + r.stderr)[-800:]})
             continue
@@ -117,6 +134,11 @@ def main():
                         if flops and dur > 0:
                             e["achieved_tflops"] = flops / dur / 1e12
                             e["roofline_frac"] = flops / dur / 1e12 / FP64_PEAK_TFLOPS
+                    elif bound == "int8":
+                        e["int8_ops"] = amount
+                        if dur > 0:
+                            e["achieved_pops"] = amount / dur / 1e15
+                            e["roofline_frac"] = amount / dur / 1e15 / INT8_PEAK_POPS
                     else:
                         by = amount if amount is not None else num(e.get("dram__bytes_write.sum", "0 byte"))
                         e["algorithmic_bytes"] = by
@@ -126,8 +148,11 @@ def main():
                     break
             result.append(e)
             print(nm, e["kernel"][:70], e.get("gpu__time_duration.sum"), "frac", e.get("roofline_frac"), flush=True)
-    json.dump({"peaks": {"fp64_tflops": FP64_PEAK_TFLOPS, "hbm_gbs": HBM_PEAK_GBS}, "kernels": result},
-              open(args.out, "w"), indent=1)
+    if args.merge and os.path.exists(args.merge):   # replace the entries of the re-run workloads, keep the rest
+        old = json.load(open(args.merge))["kernels"]
+        result = [e for e in old if e.get("workload") not in names] + result
+    json.dump({"peaks": {"fp64_tflops": FP64_PEAK_TFLOPS, "hbm_gbs": HBM_PEAK_GBS, "int8_pops_nominal": INT8_PEAK_POPS},
+               "kernels": result}, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":

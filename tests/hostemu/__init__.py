@@ -39,6 +39,21 @@ class HostEmu:
         i, d = C.c_int, C.c_double
         self.lib.emu_cos.argtypes = [i, i, _dp, i, _dp, i, d, d, _dp, i, i, i, i, i, _dp]
         self.lib.emu_logcf.argtypes = [i, i, _dp, d, d, d, d, _dp]
+        self.lib.emu_q8_store.argtypes = [_dp, _dp, i, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def q8_store(self, re, im):
+        """Digit planes of the int8 contraction for n complex values: (q_re, q_im, rowflag, planes)."""
+        re = np.ascontiguousarray(re, dtype=np.float64)
+        im = np.ascontiguousarray(im, dtype=np.float64)
+        n = re.size
+        planes = np.zeros((n, 6, 2), dtype=np.uint8)
+        flag = np.zeros(n, dtype=np.uint8)
+        qr = np.zeros(n, dtype=np.int64)
+        qi = np.zeros(n, dtype=np.int64)
+        rc = self.lib.emu_q8_store(re.ctypes.data_as(_dp), im.ctypes.data_as(_dp), n, planes.ctypes.data,
+                                   flag.ctypes.data, qr.ctypes.data, qi.ctypes.data)
+        assert rc == 0
+        return qr, qi, flag, planes
 
     def cos(self, base, tc, params, K, S0, r, T, numU, kind=0, use_tgrid=True, fast=True):
         K = np.ascontiguousarray(K, dtype=np.float64)

@@ -106,3 +106,27 @@ extern "C" int emu_logcf(int base, int tc, const double* params, double r, doubl
   out2[1] = l.y;
   return 0;
 }
+
+// Digit-plane store of the int8 contraction (cos_coeff.cuh: coeff_store(Q8Row), the very code the
+// quantising coefficient kernels run): n complex values -> [n][6][Kp = 1] byte pairs + row flags, and
+// the integers the six signed digits reassemble to.
+extern "C" int emu_q8_store(const double* re, const double* im, int n, unsigned char* planes,
+                            unsigned char* rowflag, long long* q_re, long long* q_im) {
+  CosCoeffArgs a{};
+  a.Kp = 1;
+  a.C8 = planes;
+  a.rowflag = rowflag;
+  for (int i = 0; i < n; ++i) {
+    Q8Row row;
+    row.p = reinterpret_cast<unsigned short*>(planes) + (size_t)i * Q8_SLICES;
+    coeff_store(a, row, 0, 1, re[i], im[i]);
+    long long qr = 0, qi = 0;
+    for (int s = Q8_SLICES - 1; s >= 0; --s) {
+      qr = qr * 256 + (signed char)planes[((size_t)i * Q8_SLICES + s) * 2];
+      qi = qi * 256 + (signed char)planes[((size_t)i * Q8_SLICES + s) * 2 + 1];
+    }
+    q_re[i] = qr;
+    q_im[i] = qi;
+  }
+  return 0;
+}

@@ -170,3 +170,32 @@ def test_i8_wide_strike_range(engine, best_oracle, monkeypatch):
     assert np.all(np.abs(i8 - f64) <= 1e-12 * K[None, None, :] + 1e-12)
     ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, T, 512, 0)
     assert_parity(i8, ref, what="wide strike range")
+
+
+def test_i8_chunked_batches_are_bit_identical(engine, monkeypatch):
+    """FOP_COS_CHUNK_MIB=1 forces ~30 chunks of parameter sets (each with its own digit planes, row
+    flags and tensor map): same bits as the single-chunk call, NaN rows included."""
+    prm = CASES.heston_batch(900)
+    prm[611, 1] = np.nan
+    K, T = CASES.c5_strikes(), list(CASES.C5_T)
+    mkt = np.array([[CASES.bs_call(100.0, 1.0, k, 0.25, t) for k in K] for t in T])
+    w = CASES.c5_weights()
+    monkeypatch.delenv("FOP_GEMM_I8", raising=False)
+    one_l, one_p = engine.cos_loss(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.0, T, 256, mkt, w, want_prices=True)
+    assert engine.last_cos_contraction == "int8-tcgen05"
+    monkeypatch.setenv("FOP_COS_CHUNK_MIB", "1")
+    many_l, many_p = engine.cos_loss(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.0, T, 256, mkt, w, want_prices=True)
+    assert np.array_equal(one_p, many_p, equal_nan=True) and np.array_equal(one_l, many_l, equal_nan=True)
+    assert np.all(np.isnan(one_p[611])) and np.isnan(one_l[611]) and np.isfinite(np.delete(one_l, 611)).all()
+
+
+def test_i8_u_count_limit_falls_back(engine, best_oracle):
+    """numU > 8192 (more than 16 384 terms per int32 accumulator) takes the fp64 kernels."""
+    prm = CASES.heston_batch(2)
+    K = 100.0 * np.linspace(1.4, 0.6, 9)
+    got = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, [1.0], 8192, 0)
+    assert engine.last_cos_contraction == "int8-tcgen05"
+    ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, [1.0], 8192, 0)
+    assert_parity(got, ref, what="numU=8192")
+    engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, [1.0], 8200, 0)
+    assert engine.last_cos_contraction == "fp64-dmma"

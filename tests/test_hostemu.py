@@ -97,3 +97,24 @@ def test_emulated_variance_gamma_vs_oracle_and_40_digit_reference(emu, best_orac
         ref = best_oracle.cos(3, tc, prm2, K, 100.0, .05, T, 128, 0)
         got = emu.cos(3, tc, prm2, K, 100.0, .05, T, 128, 0)
         assert _ratio(got, ref).max() <= 1.0, tc
+
+
+def test_q8_digit_planes_round_to_nearest_and_flag_the_unrepresentable(emu):
+    """The quantiser of the int8 contraction (cos_coeff.cuh::coeff_store(Q8Row), same source as the
+    device): six signed base-256 digits reassemble to rint(x) (ties to even) for |x| < 2^46 -- twice the
+    nominal coefficient range 2^45 -- and NaN / out-of-range values flag their row and store zeros."""
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(-2.0**45, 2.0**45, 20000), rng.uniform(-300.0, 300.0, 2000),
+                        [0.0, -0.0, 0.5, 1.5, 2.5, -0.5, -1.5, 127.5, 128.5, -128.5, 32767.5, 2.0**45, -2.0**45,
+                         2.0**46 - 2.0**33, -(2.0**46 - 2.0**33)]])
+    y = x[::-1].copy()
+    qr, qi, flag, planes = emu.q8_store(x, y)
+    assert not flag.any()
+    assert np.array_equal(qr, np.rint(x).astype(np.int64))
+    assert np.array_equal(qi, np.rint(y).astype(np.int64))
+    bad = np.array([np.nan, np.inf, -np.inf, 2.0**46 + 2.0**33, -2.0**47, 1e300, 3.0])
+    qr, qi, flag, planes = emu.q8_store(bad, np.zeros_like(bad))
+    assert flag.tolist() == [1, 1, 1, 1, 1, 1, 0]
+    assert not planes[:6].any() and qr[6] == 3
+    qr, qi, flag, _ = emu.q8_store(np.array([1.0, 2.0]), np.array([np.nan, 5.0]))   # one bad component flags the pair
+    assert flag.tolist() == [1, 0] and qr[1] == 2 and qi[1] == 5
