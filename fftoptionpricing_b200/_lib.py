@@ -89,7 +89,8 @@ _SIGNATURES = {
     "fop_measure_fp64_peak": (C.c_int, [C.c_void_p, _dp]),
 }
 # not part of the public header: tuning probe used by profiles/ scripts
-_PRIVATE = {"fop_microbench_fp64": (C.c_int, [C.c_void_p, _dp])}
+_PRIVATE = {"fop_microbench_fp64": (C.c_int, [C.c_void_p, _dp]),
+            "fop_microbench_int8": (C.c_int, [C.c_void_p, _dp])}
 
 _lib = None
 

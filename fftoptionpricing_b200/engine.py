@@ -140,6 +140,12 @@ class Engine:
         self._check(self._L.fop_microbench_fp64(self._h, v))
         return list(v)
 
+    def microbench_int8(self):
+        """Measured tcgen05.mma kind::i8 rate (POP/s) with shared-memory-resident operands."""
+        v = C.c_double()
+        self._check(self._L.fop_microbench_int8(self._h, C.byref(v)))
+        return v.value
+
     @staticmethod
     def _params(base, tc, params):
         np_ = num_params(base, tc)

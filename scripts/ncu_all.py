@@ -22,7 +22,7 @@ from ncu_summary import opcode_mix, summarise  # noqa: E402
 
 FP64_PEAK_TFLOPS = 37.0   # DMMA probe of fop_microbench_fp64 on B200 (bench.py re-measures it live)
 HBM_PEAK_GBS = 6554.6     # MEASURED_PEAKS.json
-INT8_PEAK_POPS = 4.5      # nominal dense int8 tensor rate of B200 (no measured entry)
+INT8_PEAK_POPS = 4.45     # fop_microbench_int8 on B200 (tcgen05.mma kind::i8, smem-resident operands); nominal 4.5
 PROF_NAME = {"c5i8": "c5", "c2i8": "c2"}            # workload of scripts/prof_workloads.py
 ENV = {"c5": {"FOP_GEMM_I8": "0"}, "c2": {"FOP_GEMM_I8": "0"}}
 
