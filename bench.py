@@ -323,7 +323,10 @@ def extra_configs(eng, torch, dev, peak, stream):
                  "value": P * 1024 / (ms * 1e-3), "unit": UNIT,
                  "roofline": {"bound": "tensor", "algorithmic_flops": fl, "achieved": fl / (ms * 1e-3) / 1e12,
                               "peak": peak, "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / peak,
-                              "what": "4 numU flops per price over the whole call (coefficient + contraction kernels)"}}
+                              "what": "4 numU flops per price over the whole call (coefficient + contraction kernels) "
+                                      "against the fp64 peak; fp64-EQUIVALENT (may exceed 1) when the contraction "
+                                      "runs as exact int8 digit planes on tcgen05",
+                              "contraction": eng.last_cos_contraction}}
     del o
     # C3: Merton American put FSTS, N = 4096, 256 steps, 4096 sets
     P = 4096
