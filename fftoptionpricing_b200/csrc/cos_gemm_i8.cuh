@@ -34,17 +34,18 @@
 //             max(0, 4 - s) .. 5 lie contiguously in shared memory (72 rows each) and their levels
 //             contiguously in TMEM (72 columns each), so two planes are multiplied by ONE instruction
 //             of N = 144; an odd last plane (always plane 5) takes N = 80, reading eight zero rows
-//             behind plane 5 and adding zeros to the first eight columns of the next level.  Thirteen
+//             behind plane 5 and adding zeros to the first eight columns of the next level.  Fourteen
 //             instructions per 32 kk instead of 26.  tcgen05.commit releases the stage / publishes
 //             the accumulators.
 //   (more than 72 strikes: blockIdx.y walks blocks of 72 columns, each a pass over the coefficient planes)
 //   warps 2-9 epilogue (a warp reads TMEM lanes 32 (warp % 4) .. +31; two warps share a lane quarter
 //             and take 36 columns each): tcgen05.ld the seven level accumulators, write zeros back
 //             (tcgen05.st: every MMA accumulates, no first-instruction special case), recombine in
-//             integer (two halves of at most 50 bits), convert -- then hand TMEM back to the tensor
+//             integer (three groups below 2^48, exact for any int32 accumulators), convert -- then
+//             hand TMEM back to the tensor
 //             core and only afterwards run the price map + squared-error loss of the fp64 kernel from
 //             the 36 doubles held in registers (measured: the tile period fell from 29 000 to
-//             ~24 000 cycles against 21 000 with no epilogue at all).
+//             ~25 000 cycles against 21 000 with no epilogue at all).
 // TMEM: 7 levels x 72 columns = 504 (+8 overlap) of the 512 columns.
 #pragma once
 #include <cuda.h>
