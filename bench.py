@@ -501,6 +501,26 @@ def run_ours(args):
         prof = eng.profile_read()
         eng.profile_enable(False)
         contraction = eng.last_cos_contraction   # (before the extra configurations run other shapes)
+        # ---- the same step with EVERY kernel in fp64 (FOP_GEMM_I8=0: fp64 tensor-core contraction), for a
+        # reader who wants the all-fp64 figure next to the default (exact int8 digit planes, DESIGN.md
+        # decision 12); untimed warm-up, then `steps` steps, device resident, this rank
+        all_fp64 = None
+        if contraction == "int8-tcgen05":
+            os.environ["FOP_GEMM_I8"] = "0"
+            for i in range(3):
+                step_device(i)
+            finish_device()
+            torch.cuda.synchronize(dev)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(args.steps):
+                step_device(i)
+            finish_device()
+            e1.record(stream)
+            torch.cuda.synchronize(dev)
+            all_fp64 = e0.elapsed_time(e1) / args.steps
+            os.environ.pop("FOP_GEMM_I8", None)
         peaks = eng.microbench_fp64() if rank == 0 else None
         i8_peak = eng.microbench_int8() if rank == 0 else None
 
@@ -664,6 +684,15 @@ def run_ours(args):
             line["sustained"] = {"seconds": sus_ms * 1e-3, "steps": n_sus, "ms_per_step": sus_ms / n_sus,
                                  "value": prices_per_step * n_sus / (sus_ms * 1e-3), "unit": UNIT,
                                  "clocks": sustained[2]}
+        if all_fp64:
+            line["all_fp64"] = {
+                "ms_per_step": all_fp64, "value": P * M * COUNTED_STRIKES / (all_fp64 * 1e-3), "unit": UNIT,
+                "n_gpus": 1,
+                "what": "the same step on this rank with FOP_GEMM_I8=0: the contraction on the fp64 tensor cores "
+                        "(mma.sync DMMA) like every other kernel.  The default contraction is exact integer "
+                        "arithmetic on 46-bit fixed-point operands; the two agree to <= 1.7e-10 over 66 M prices "
+                        "(rms 4e-12) -- less than either differs from the CPU reference (3e-10 = 0.03 of the "
+                        "1e-8 + 1e-10 |ref| bar, profiles/r2_parity_sweeps_gpu.log)"}
         if strong:
             line["strong_scaling_anchor"] = strong
         if extra:
