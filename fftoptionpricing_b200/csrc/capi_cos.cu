@@ -151,12 +151,13 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const int Jp = fused ? dm_bs(fnb) : gx ? JB + 2 : nblk * JB;  // row stride of the basis table
   // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
   const int KK = ((2 * numU + Q8_KC - 1) / Q8_KC) * Q8_KC;  // (a multiple of DM_KC, TM_KC and FW_KC too)
-  // int8 tensor-core contraction (cos_gemm_i8.cuh): call / put prices (and the loss) of a model CF with
+  // int8 tensor-core contraction (cos_gemm_i8.cuh): call / put prices, deltas and gammas (one kind per
+  // call; and the loss) of a model CF with
   // up to 16 maturities (market tables of a strike block in shared memory) and numU <= 8192 (int32
   // accumulators cannot overflow); everything else, or
   // FOP_GEMM_I8=0, takes the fp64 tensor-core kernels
   const int nblk8 = (J + Q8_NQ - 1) / Q8_NQ, J8 = nblk8 * Q8_NQ;
-  bool use_i8 = !fused && !cf_samples && nk == 1 && kinds[0] <= 1 && cos_i8_smem(M) + 512 <= h->smem_optin && KK <= 16384 &&
+  bool use_i8 = !fused && !cf_samples && nk == 1 && kinds[0] <= 5 && cos_i8_smem(M) + 512 <= h->smem_optin && KK <= 16384 &&
                 tmap_encoder() != nullptr;
   if (const char* e = std::getenv("FOP_GEMM_I8"))
     if (e[0] == '0') use_i8 = false;
@@ -199,10 +200,9 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       uk[k] = du * k;
       vk[k] = vk_put(xMin, uk[k], k) * cp * (k == 0 ? 0.5 : 1.0);
     }
-    double amax = 0.0;
-    for (int k = 0; k < numU; ++k) amax = std::max(amax, std::fabs(vk[k]));
-    cc.amax = amax;
-    const size_t bytes = (tab_doubles + (size_t)KK * Jp + numU) * 8 + 512 + (size_t)Q8_SLICES * J8 * KK;
+    cc.vk_host.assign(vk, vk + numU);
+    cc.uk_host.assign(uk, uk + numU);
+    const size_t bytes = (tab_doubles + (size_t)KK * Jp + 2 * (size_t)numU) * 8 + 512 + (size_t)Q8_SLICES * J8 * KK;
     FOP_CUDA(h, cudaStreamSynchronize(h->stream));  // earlier launches may still read the old tables
     if (cc.bytes < bytes) {
       if (cc.dev) cudaFree(cc.dev);
@@ -221,21 +221,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
                                                                Jp, cc.dev + boff);
     }
     FOP_LAUNCH_CHECK(h);
-    {  // fixed-point tables of the int8 contraction: vk 2^45 / amax, basis digit planes
-      std::vector<double> vk8(numU);
-      for (int k = 0; k < numU; ++k) vk8[k] = vk[k] > 0.0 ? Q8_A_SCALE : vk[k] < 0.0 ? -Q8_A_SCALE : 0.0;
-      double* d_vk8 = cc.dev + boff + (size_t)KK * Jp;
-      FOP_CUDA(h, cudaMemcpy(d_vk8, vk8.data(), sizeof(double) * numU, cudaMemcpyHostToDevice));
-      unsigned char* d_b8 = reinterpret_cast<unsigned char*>(
-          (reinterpret_cast<uintptr_t>(d_vk8 + numU) + 255) & ~(uintptr_t)255);
-      const long long n8 = (long long)J8 * KK;
-      if (amax > 0.0) {
-        ProfScope ps(h, "cos_basis_q8_kernel");
-        cos_basis_q8_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, h->stream>>>(cc.dev + boff, cc.dev + numU,
-                                                                                 1.0 / amax, numU, KK, Jp, J, J8, d_b8);
-      }
-      FOP_LAUNCH_CHECK(h);
-    }
+    cc.q8_greek = -1;  // the fixed-point tables of the int8 contraction are rebuilt below
     cc.K = Kh;  cc.T = Th;  cc.S0 = S0;  cc.numU = numU;  cc.JB = JB;  cc.Jp = Jp;  cc.KK = KK;
   }
   const double* d_tab = cc.dev;
@@ -243,10 +229,42 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const double* d_T = cc.dev + 2 * numU + 2 * J;
   const int* d_npow = cc.dt > 0.0 ? reinterpret_cast<const int*>(cc.dev + npow_off) : nullptr;
   const double* d_basis = cc.dev + ((tab_doubles + 1) & ~(size_t)1);
-  const double* d_vk8 = d_basis + (size_t)KK * Jp;
-  const unsigned char* d_b8 = reinterpret_cast<const unsigned char*>(
-      (reinterpret_cast<uintptr_t>(d_vk8 + numU) + 255) & ~(uintptr_t)255);
-  if (cc.amax <= 0.0) use_i8 = false;
+  double* d_vk8 = cc.dev + ((tab_doubles + 1) & ~(size_t)1) + (size_t)KK * Jp;   // [numU] v of the quantising kernel
+  double* d_wk8 = d_vk8 + numU;                                                   // [numU] basis row weights
+  unsigned char* d_b8 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(d_wk8 + numU) + 255) & ~(uintptr_t)255);
+  // Fixed-point tables of the int8 contraction for the transform g = kind / 2 (0 price, 1 delta,
+  // 2 gamma; OptionPricing.h:44-73): the transform multiplies phi by f_k e^{i arg}, f_k = 1, u_k,
+  // u_k sqrt(1 + u_k^2).  The quantising kernel stores (phi * factor) * v with v = sign(V_k) 2^45 / f_k
+  // -- a unit-modulus multiple of phi -- and the magnitude |V_k cp| f_k / amax moves to the basis
+  // planes.  Rebuilt when the strike grid or the transform changes.
+  const int q8g = kinds[0] >> 1;
+  if (use_i8 && cc.q8_greek != q8g) {
+    std::vector<double> v8(numU), w8(numU);
+    double amax = 0.0;
+    for (int k = 0; k < numU; ++k) {
+      const double u = cc.uk_host[k];
+      const double f = q8g == 0 ? 1.0 : q8g == 1 ? u : u * std::sqrt(1.0 + u * u);
+      w8[k] = std::fabs(cc.vk_host[k]) * f;
+      v8[k] = (f > 0.0 && cc.vk_host[k] != 0.0) ? std::copysign(Q8_A_SCALE / f, cc.vk_host[k]) : 0.0;
+      amax = std::max(amax, w8[k]);
+    }
+    cc.amax = amax;
+    if (amax > 0.0 && std::isfinite(amax)) {
+      for (int k = 0; k < numU; ++k) w8[k] /= amax;
+      FOP_CUDA(h, cudaStreamSynchronize(h->stream));  // earlier launches may still read the old tables
+      FOP_CUDA(h, cudaMemcpy(d_vk8, v8.data(), sizeof(double) * numU, cudaMemcpyHostToDevice));
+      FOP_CUDA(h, cudaMemcpy(d_wk8, w8.data(), sizeof(double) * numU, cudaMemcpyHostToDevice));
+      const long long n8 = (long long)J8 * KK;
+      {
+        ProfScope ps(h, "cos_basis_q8_kernel");
+        cos_basis_q8_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, h->stream>>>(d_basis, d_wk8, numU, KK, Jp, J, J8,
+                                                                                 d_b8);
+      }
+      FOP_LAUNCH_CHECK(h);
+      cc.q8_greek = q8g;
+    }
+  }
+  if (use_i8 && (cc.q8_greek != q8g || !(cc.amax > 0.0))) use_i8 = false;
   if (use_i8) nblk = 2 * nblk8;  // two partial row losses per (set, maturity, strike block): one per column half
 
   const bool out_host = out && !is_device_ptr(out);

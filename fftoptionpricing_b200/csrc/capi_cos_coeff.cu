@@ -17,13 +17,17 @@ bool cos_coeff_launch_spec(fop_handle_t h, const CosCoeffArgs& a_in, int grid_bl
   if (a.M < kCoeffShapes[shape].ilp) shape = 1;
   // quantised output (cos_gemm_i8.cuh); 102: a.Kp == 256 compiled in (GAUSS + CIR on a maturity grid)
   if (a.C8) shape = shape == 1 ? ((a.Kp == 256 && a.base == BASE_GAUSS && a.tc == TC_CIR && a.npow) ? 102 : 101) : 100;
-  const bool grid = a.npow != nullptr, price_only = a.greek_mask == 1;
+  if (a.C8 && a.greek_mask != 1) shape = 100;
+  const bool grid = a.npow != nullptr;
+  // one compile-time transform: price (both outputs), or delta / gamma with the quantised output
+  const int gsel = a.greek_mask == 1 ? 1 : (a.C8 && (a.greek_mask == 2 || a.greek_mask == 4)) ? a.greek_mask : -1;
+  if (a.C8 && gsel < 0) return false;
   int nt = 256;
   CoeffKernel k = nullptr;
-  if (a.base == BASE_GAUSS) k = coeff_pick_gauss(a.tc, grid, price_only, shape, &nt);
-  else if (a.base == BASE_MERTON) k = coeff_pick_merton(a.tc, grid, price_only, shape, &nt);
-  else if (a.base == BASE_CGMY) k = coeff_pick_cgmy(a.tc, grid, price_only, shape, &nt);
-  else if (a.base == BASE_VG) k = coeff_pick_vg(a.tc, grid, price_only, shape, &nt);
+  if (a.base == BASE_GAUSS) k = coeff_pick_gauss(a.tc, grid, gsel, shape, &nt);
+  else if (a.base == BASE_MERTON) k = coeff_pick_merton(a.tc, grid, gsel, shape, &nt);
+  else if (a.base == BASE_CGMY) k = coeff_pick_cgmy(a.tc, grid, gsel, shape, &nt);
+  else if (a.base == BASE_VG) k = coeff_pick_vg(a.tc, grid, gsel, shape, &nt);
   if (!k) return false;
   // sets per CTA: four (set, u) pairs per thread, whole sets only
   a.spb = std::max(1, std::min(COEFF_MAX_SPB, 4 * nt / a.Kp));

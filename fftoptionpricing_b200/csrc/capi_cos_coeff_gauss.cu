@@ -1,7 +1,7 @@
 // Specialised COS coefficient kernels, Levy base GAUSS (cos_coeff_launch.cuh).
 #include "cos_coeff_launch.cuh"
 namespace fop {
-CoeffKernel coeff_pick_gauss(int tc, bool grid, bool price_only, int shape, int* nt) {
-  return coeff_pick_base<BASE_GAUSS>(tc, grid, price_only, shape, nt);
+CoeffKernel coeff_pick_gauss(int tc, bool grid, int gsel, int shape, int* nt) {
+  return coeff_pick_base<BASE_GAUSS>(tc, grid, gsel, shape, nt);
 }
 }  // namespace fop

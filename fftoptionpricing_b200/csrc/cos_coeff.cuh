@@ -172,7 +172,15 @@ __host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, cons
     for (int i = 0; i < N; ++i) coeff_store(a, crow, i, Kp, t.x.v[i], t.y.v[i]);
     return;
   }
-  if constexpr (std::is_same<CP, double2*>::value) {  // (the quantised output exists for prices only)
+  if constexpr (std::is_same<CP, Q8Row>::value) {
+    // quantised output of ONE transform (GMASK = 2 delta, 4 gamma): v carries 2^45 / |transform factor|,
+    // so the stored value is phi times a unit-modulus factor (cos_gemm_i8.cuh)
+    static_assert(GMASK == 1 || GMASK == 2 || GMASK == 4, "quantised output: price, delta or gamma");
+    const cx<VD<N>> d = cexp(lphi);
+    const cx<VD<N>> t = option_transform(GMASK == 2 ? 1 : 2, d, u, a.r);
+#pragma unroll
+    for (int i = 0; i < N; ++i) coeff_store(a, crow, i, Kp, t.x.v[i] * v, t.y.v[i] * v);
+  } else {
     const cx<VD<N>> d = cexp(lphi);
     // one CF evaluation feeds every requested transform (price / delta / gamma / theta)
     double2* cg = crow;

@@ -16,7 +16,14 @@ constexpr int kNumCoeffShapes = sizeof(kCoeffShapes) / sizeof(kCoeffShapes[0]);
 
 template <int BASE, int TC, bool GRID, int GMASK>
 CoeffKernel coeff_pick_shape(int shape, int* nt) {
-  // shape >= 100: quantised output (digit planes for the int8 contraction; price only)
+  // shape >= 100: quantised output (digit planes for the int8 contraction; one transform)
+  if constexpr (GMASK == 2 || GMASK == 4) {
+    if (shape >= 100) {
+      *nt = 256;
+      return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 256, 2, true, true>;
+    }
+    return nullptr;
+  }
   if constexpr (GMASK == 1) {
     if (shape >= 100) {
       if constexpr (BASE == BASE_GAUSS && TC == TC_CIR && GRID) {
@@ -36,26 +43,36 @@ CoeffKernel coeff_pick_shape(int shape, int* nt) {
   return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 256, 2>;
 }
 
+// gsel: -1 = run-time transform mask (fp64 output), 1 = price only, 2 / 4 = delta / gamma only (the
+// latter two exist with the quantised output only)
+template <int BASE, int TC, bool GRID>
+CoeffKernel coeff_pick_mask(int gsel, int shape, int* nt) {
+  if (gsel == 1) return coeff_pick_shape<BASE, TC, GRID, 1>(shape, nt);
+  if (gsel == 2) return coeff_pick_shape<BASE, TC, GRID, 2>(shape, nt);
+  if (gsel == 4) return coeff_pick_shape<BASE, TC, GRID, 4>(shape, nt);
+  return coeff_pick_shape<BASE, TC, GRID, -1>(shape, nt);
+}
+
 template <int BASE, int TC>
-CoeffKernel coeff_pick_tc(bool grid, bool price_only, int shape, int* nt) {
+CoeffKernel coeff_pick_tc(bool grid, int gsel, int shape, int* nt) {
   if constexpr (TC == TC_NONE) {
-    return price_only ? coeff_pick_shape<BASE, TC, false, 1>(shape, nt) : coeff_pick_shape<BASE, TC, false, -1>(shape, nt);
+    return coeff_pick_mask<BASE, TC, false>(gsel, shape, nt);
   } else {
-    if (grid) return price_only ? coeff_pick_shape<BASE, TC, true, 1>(shape, nt) : coeff_pick_shape<BASE, TC, true, -1>(shape, nt);
-    return price_only ? coeff_pick_shape<BASE, TC, false, 1>(shape, nt) : coeff_pick_shape<BASE, TC, false, -1>(shape, nt);
+    if (grid) return coeff_pick_mask<BASE, TC, true>(gsel, shape, nt);
+    return coeff_pick_mask<BASE, TC, false>(gsel, shape, nt);
   }
 }
 
 template <int BASE>
-CoeffKernel coeff_pick_base(int tc, bool grid, bool price_only, int shape, int* nt) {
-  if (tc == TC_NONE) return coeff_pick_tc<BASE, TC_NONE>(grid, price_only, shape, nt);
-  if (tc == TC_CIR) return coeff_pick_tc<BASE, TC_CIR>(grid, price_only, shape, nt);
-  return coeff_pick_tc<BASE, TC_CIR_DIFFUSION>(grid, price_only, shape, nt);
+CoeffKernel coeff_pick_base(int tc, bool grid, int gsel, int shape, int* nt) {
+  if (tc == TC_NONE) return coeff_pick_tc<BASE, TC_NONE>(grid, gsel, shape, nt);
+  if (tc == TC_CIR) return coeff_pick_tc<BASE, TC_CIR>(grid, gsel, shape, nt);
+  return coeff_pick_tc<BASE, TC_CIR_DIFFUSION>(grid, gsel, shape, nt);
 }
 
-CoeffKernel coeff_pick_gauss(int tc, bool grid, bool price_only, int shape, int* nt);
-CoeffKernel coeff_pick_merton(int tc, bool grid, bool price_only, int shape, int* nt);
-CoeffKernel coeff_pick_cgmy(int tc, bool grid, bool price_only, int shape, int* nt);
-CoeffKernel coeff_pick_vg(int tc, bool grid, bool price_only, int shape, int* nt);
+CoeffKernel coeff_pick_gauss(int tc, bool grid, int gsel, int shape, int* nt);
+CoeffKernel coeff_pick_merton(int tc, bool grid, int gsel, int shape, int* nt);
+CoeffKernel coeff_pick_cgmy(int tc, bool grid, int gsel, int shape, int* nt);
+CoeffKernel coeff_pick_vg(int tc, bool grid, int gsel, int shape, int* nt);
 
 }  // namespace fop

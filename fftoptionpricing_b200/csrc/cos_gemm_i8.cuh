@@ -96,13 +96,13 @@ __host__ inline size_t cos_i8_smem(int M) {
 
 // basis digit planes B8[6][J8][KK] (K-major: one row of KK bytes per strike; J8 = strike count padded
 // to whole 72-column blocks) from basis[KK][Jp], row kk weighted by |V_k cp| / amax (scaling note above)
-static __global__ void cos_basis_q8_kernel(const double* __restrict__ basis, const double* __restrict__ vk,
-                                           double inv_amax, int numU, int KK, int Jp, int J, int J8,
+static __global__ void cos_basis_q8_kernel(const double* __restrict__ basis, const double* __restrict__ wk,
+                                           int numU, int KK, int Jp, int J, int J8,
                                            unsigned char* __restrict__ B8) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= J8 * KK) return;
   const int j = idx / KK, kk = idx - j * KK;
-  const double v = (j < J && kk < 2 * numU) ? basis[(size_t)kk * Jp + j] * (fabs(vk[kk >> 1]) * inv_amax) : 0.0;
+  const double v = (j < J && kk < 2 * numU) ? basis[(size_t)kk * Jp + j] * wk[kk >> 1] : 0.0;
   unsigned lo, hi;
   q8_digits(v * Q8_B_SCALE, lo, hi);   // |v| <= 1: always representable
   const unsigned long long u = lo | ((unsigned long long)hi << 32);
