@@ -151,13 +151,13 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const int Jp = fused ? dm_bs(fnb) : gx ? JB + 2 : nblk * JB;  // row stride of the basis table
   // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
   const int KK = ((2 * numU + Q8_KC - 1) / Q8_KC) * Q8_KC;  // (a multiple of DM_KC, TM_KC and FW_KC too)
-  // int8 tensor-core contraction (cos_gemm_i8.cuh): call / put prices, deltas and gammas (one kind per
-  // call; and the loss) of a model CF with
+  // int8 tensor-core contraction (cos_gemm_i8.cuh): any ONE output kind per call (and the loss) of a
+  // model CF with
   // up to 16 maturities (market tables of a strike block in shared memory) and numU <= 8192 (int32
   // accumulators cannot overflow); everything else, or
   // FOP_GEMM_I8=0, takes the fp64 tensor-core kernels
   const int nblk8 = (J + Q8_NQ - 1) / Q8_NQ, J8 = nblk8 * Q8_NQ;
-  bool use_i8 = !fused && !cf_samples && nk == 1 && kinds[0] <= 5 && cos_i8_smem(M) + 512 <= h->smem_optin && KK <= 16384 &&
+  bool use_i8 = !fused && !cf_samples && nk == 1 && cos_i8_smem(M) + 512 <= h->smem_optin && KK <= 16384 &&
                 tmap_encoder() != nullptr;
   if (const char* e = std::getenv("FOP_GEMM_I8"))
     if (e[0] == '0') use_i8 = false;
@@ -233,17 +233,18 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   double* d_wk8 = d_vk8 + numU;                                                   // [numU] basis row weights
   unsigned char* d_b8 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(d_wk8 + numU) + 255) & ~(uintptr_t)255);
   // Fixed-point tables of the int8 contraction for the transform g = kind / 2 (0 price, 1 delta,
-  // 2 gamma; OptionPricing.h:44-73): the transform multiplies phi by f_k e^{i arg}, f_k = 1, u_k,
-  // u_k sqrt(1 + u_k^2).  The quantising kernel stores (phi * factor) * v with v = sign(V_k) 2^45 / f_k
+  // 2 gamma, 3 theta; OptionPricing.h:44-73): the transform multiplies phi by a factor of modulus (at
+  // most) f_k = 1, u_k, u_k sqrt(1 + u_k^2), 4 + |r|.  The quantising kernel stores (phi * factor) * v with v = sign(V_k) 2^45 / f_k
   // -- a unit-modulus multiple of phi -- and the magnitude |V_k cp| f_k / amax moves to the basis
   // planes.  Rebuilt when the strike grid or the transform changes.
   const int q8g = kinds[0] >> 1;
-  if (use_i8 && cc.q8_greek != q8g) {
+  if (use_i8 && (cc.q8_greek != q8g || (q8g == 3 && cc.q8_r != r))) {
     std::vector<double> v8(numU), w8(numU);
     double amax = 0.0;
     for (int k = 0; k < numU; ++k) {
       const double u = cc.uk_host[k];
-      const double f = q8g == 0 ? 1.0 : q8g == 1 ? u : u * std::sqrt(1.0 + u * u);
+      // theta: -(log phi - r) phi, bounded by 1/e + pi + |r| for |phi| <= 1 (a constant "modulus")
+      const double f = q8g == 0 ? 1.0 : q8g == 1 ? u : q8g == 2 ? u * std::sqrt(1.0 + u * u) : 4.0 + std::fabs(r);
       w8[k] = std::fabs(cc.vk_host[k]) * f;
       v8[k] = (f > 0.0 && cc.vk_host[k] != 0.0) ? std::copysign(Q8_A_SCALE / f, cc.vk_host[k]) : 0.0;
       amax = std::max(amax, w8[k]);
@@ -262,6 +263,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       }
       FOP_LAUNCH_CHECK(h);
       cc.q8_greek = q8g;
+      cc.q8_r = r;
     }
   }
   if (use_i8 && (cc.q8_greek != q8g || !(cc.amax > 0.0))) use_i8 = false;

@@ -173,11 +173,12 @@ __host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, cons
     return;
   }
   if constexpr (std::is_same<CP, Q8Row>::value) {
-    // quantised output of ONE transform (GMASK = 2 delta, 4 gamma): v carries 2^45 / |transform factor|,
-    // so the stored value is phi times a unit-modulus factor (cos_gemm_i8.cuh)
-    static_assert(GMASK == 1 || GMASK == 2 || GMASK == 4, "quantised output: price, delta or gamma");
+    // quantised output of ONE transform (GMASK = 2 delta, 4 gamma, 8 theta): v carries 2^45 / (bound of
+    // the transform factor), so the stored value is phi times a factor of modulus <= 1 (cos_gemm_i8.cuh;
+    // theta: |phi (log phi - r)| <= 1/e + pi + |r| for |phi| <= 1)
+    static_assert(GMASK == 1 || GMASK == 2 || GMASK == 4 || GMASK == 8, "quantised output: one transform");
     const cx<VD<N>> d = cexp(lphi);
-    const cx<VD<N>> t = option_transform(GMASK == 2 ? 1 : 2, d, u, a.r);
+    const cx<VD<N>> t = option_transform(GMASK == 2 ? 1 : GMASK == 4 ? 2 : 3, d, u, a.r);
 #pragma unroll
     for (int i = 0; i < N; ++i) coeff_store(a, crow, i, Kp, t.x.v[i] * v, t.y.v[i] * v);
   } else {

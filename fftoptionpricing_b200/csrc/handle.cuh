@@ -34,7 +34,8 @@ struct fop_handle_s {
     double* dev = nullptr;  // [uk | vk | x | K | T | basis | vk8 | basis digit planes]
     size_t bytes = 0;
     double amax = 0;        // max_k |vk| f_k: fixed-point scale of the int8 contraction (cos_gemm_i8.cuh)
-    int q8_greek = -1;      // transform (0 price, 1 delta, 2 gamma) the int8 tables are built for
+    int q8_greek = -1;      // transform (0 price, 1 delta, 2 gamma, 3 theta) the int8 tables are built for
+    double q8_r = 0;        // ... and the rate they assume (theta's bound 4 + |r|)
     std::vector<double> uk_host, vk_host;
   } cos_cache;
   // optional NCCL communicator (capi_comm.cu; opaque here, NCCL is bound at run time)

@@ -89,7 +89,7 @@ def test_i8_strike_counts(J, engine, best_oracle, monkeypatch):
 @pytest.mark.parametrize("M,expect", [(1, "int8-tcgen05"), (16, "int8-tcgen05"), (17, "fp64-dmma"), (40, "fp64-dmma")])
 def test_i8_maturity_count_boundary(M, expect, engine, best_oracle):
     """Up to 16 maturities the market tables of a strike block fit next to the operand rings; longer
-    lists fall back to the fp64 kernels.  Theta always takes the fp64 kernels."""
+    lists fall back to the fp64 kernels, and so do calls asking for several kinds at once."""
     prm = CASES.heston_batch(3)
     K = 100.0 * np.linspace(1.5, 0.5, 30)
     T = list(np.linspace(0.1, 2.0, M))
@@ -97,7 +97,7 @@ def test_i8_maturity_count_boundary(M, expect, engine, best_oracle):
     assert engine.last_cos_contraction == expect
     ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 128, 1)
     assert_parity(got, ref, what=f"M={M}")
-    engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T[:2], 128, 6)   # call theta
+    engine.cos_greeks(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T[:2], 128, [0, 6])   # two kinds, one CF pass
     assert engine.last_cos_contraction == "fp64-dmma"
 
 
@@ -201,34 +201,35 @@ def test_i8_u_count_limit_falls_back(engine, best_oracle):
     assert engine.last_cos_contraction == "fp64-dmma"
 
 
-@pytest.mark.parametrize("kind", [2, 3, 4, 5])
-def test_i8_delta_and_gamma(kind, engine, best_oracle, monkeypatch):
-    """Call / put delta and gamma (one kind per call) through the int8 kernel: the transform factor
-    (i u, resp. -i u (1 - i u), OptionPricing.h:44-73) has its modulus moved to the basis planes, so the
-    coefficient is still a unit-modulus multiple of phi."""
+@pytest.mark.parametrize("kind", [2, 3, 4, 5, 6, 7])
+def test_i8_greeks(kind, engine, best_oracle, monkeypatch):
+    """Call / put delta, gamma and theta (one kind per call) through the int8 kernel: the transform
+    factor (i u, -i u (1 - i u), resp. -(log phi - r), OptionPricing.h:44-73) has its modulus -- for theta
+    its bound 4 + |r| -- moved to the basis planes, so the coefficient is still phi times a factor of
+    modulus at most one."""
     prm = CASES.heston_batch(33)
     K = CASES.c5_strikes()
     T = [0.25, 1.0, 2.0]
     i8, f64 = _both(engine, monkeypatch, lambda: engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.03, T, 256, kind))
     assert not np.array_equal(i8, f64), "the int8 contraction did not run"
-    scale = np.asarray(K) / (100.0 if kind < 4 else 100.0**2)      # output map: K / S0, K / S0^2
+    scale = np.asarray(K) / (100.0 if kind < 4 else 100.0**2 if kind < 6 else 0.2)   # output map: K / S0, K / S0^2, K
     assert np.all(np.abs(i8 - f64) <= 1e-10 * scale[None, None, :] + 1e-13)
     ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.03, T, 256, kind)
     assert_parity(i8, ref, what=f"int8 contraction kind {kind}")
 
 
 def test_i8_tables_follow_the_requested_kind(engine, best_oracle):
-    """price -> delta -> gamma -> price on one handle: the cached fixed-point tables are rebuilt per
-    transform; theta and multi-kind calls take the fp64 kernels."""
+    """price -> delta -> gamma -> theta -> price on one handle (and theta at another rate): the cached
+    fixed-point tables are rebuilt per transform; multi-kind calls take the fp64 kernels."""
     prm = CASES.heston_batch(6)
     K = 100.0 * np.linspace(1.5, 0.5, 24)
     T = [0.5, 1.5]
-    for kind in (0, 2, 4, 1, 3, 5, 0):
-        got = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, T, 256, kind)
+    for kind, r in ((0, 0.02), (2, 0.02), (4, 0.02), (6, 0.02), (7, 0.07), (1, 0.02), (3, 0.02), (5, 0.02), (0, 0.02)):
+        got = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, r, T, 256, kind)
         assert engine.last_cos_contraction == "int8-tcgen05"
-        ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, T, 256, kind)
+        ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, r, T, 256, kind)
         assert_parity(got, ref, what=f"kind {kind} after a table switch")
-    engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, T, 256, 6)      # call theta
+    engine.cos_greeks(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, T, 256, [0, 2, 4, 6])
     assert engine.last_cos_contraction == "fp64-dmma"
 
 
@@ -243,7 +244,7 @@ def test_i8_greeks_other_models(model, engine, best_oracle, monkeypatch):
         base, tc, prm = CASES.CGMY, CASES.TC_CIR_DIFFUSION, np.hstack([CASES.cgmy_batch(5), np.tile(cir, (5, 1))])
     K = 100.0 * np.linspace(1.4, 0.6, 31)
     T = [0.5, 1.0]
-    for kind in (2, 5):
+    for kind in (2, 5, 6):
         i8, f64 = _both(engine, monkeypatch, lambda: engine.cos(base, tc, prm, K, 100.0, 0.03, T, 256, kind))
         assert not np.array_equal(i8, f64)
         ref = best_oracle.cos(base, tc, prm, K, 100.0, 0.03, T, 256, kind)
