@@ -151,13 +151,12 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const int Jp = fused ? dm_bs(fnb) : gx ? JB + 2 : nblk * JB;  // row stride of the basis table
   // rows of C / of the basis are zero-padded to a multiple of the contraction's k-stage
   const int KK = ((2 * numU + Q8_KC - 1) / Q8_KC) * Q8_KC;  // (a multiple of DM_KC, TM_KC and FW_KC too)
-  // int8 tensor-core contraction (cos_gemm_i8.cuh): any ONE output kind per call (and the loss) of a
-  // model CF with
-  // up to 16 maturities (market tables of a strike block in shared memory) and numU <= 8192 (int32
-  // accumulators cannot overflow); everything else, or
-  // FOP_GEMM_I8=0, takes the fp64 tensor-core kernels
+  // int8 tensor-core contraction (cos_gemm_i8.cuh): every output kind of a model CF with up to 16
+  // maturities (market tables of a strike block in shared memory) and numU <= 8192 (int32 accumulators
+  // cannot overflow); sampled CFs, longer maturity lists, or FOP_GEMM_I8=0, take the fp64 tensor-core
+  // kernels
   const int nblk8 = (J + Q8_NQ - 1) / Q8_NQ, J8 = nblk8 * Q8_NQ;
-  bool use_i8 = !fused && !cf_samples && nk == 1 && cos_i8_smem(M) + 512 <= h->smem_optin && KK <= 16384 &&
+  bool use_i8 = !fused && !cf_samples && cos_i8_smem(M) + 512 <= h->smem_optin && KK <= 16384 &&
                 tmap_encoder() != nullptr;
   if (const char* e = std::getenv("FOP_GEMM_I8"))
     if (e[0] == '0') use_i8 = false;
@@ -202,7 +201,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
     }
     cc.vk_host.assign(vk, vk + numU);
     cc.uk_host.assign(uk, uk + numU);
-    const size_t bytes = (tab_doubles + (size_t)KK * Jp + 2 * (size_t)numU) * 8 + 512 + (size_t)Q8_SLICES * J8 * KK;
+    const size_t bytes = (tab_doubles + (size_t)KK * Jp + 2 * (size_t)numU) * 8 + 512 + 3 * (((size_t)Q8_SLICES * J8 * KK + 255) & ~(size_t)255);
     FOP_CUDA(h, cudaStreamSynchronize(h->stream));  // earlier launches may still read the old tables
     if (cc.bytes < bytes) {
       if (cc.dev) cudaFree(cc.dev);
@@ -221,7 +220,8 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
                                                                Jp, cc.dev + boff);
     }
     FOP_LAUNCH_CHECK(h);
-    cc.q8_greek = -1;  // the fixed-point tables of the int8 contraction are rebuilt below
+    cc.q8_valid[0] = cc.q8_valid[1] = cc.q8_valid[2] = false;  // fixed-point tables of the int8 contraction: rebuilt on demand
+    cc.q8_vp_valid = cc.q8_vt_valid = false;
     cc.K = Kh;  cc.T = Th;  cc.S0 = S0;  cc.numU = numU;  cc.JB = JB;  cc.Jp = Jp;  cc.KK = KK;
   }
   const double* d_tab = cc.dev;
@@ -229,44 +229,69 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   const double* d_T = cc.dev + 2 * numU + 2 * J;
   const int* d_npow = cc.dt > 0.0 ? reinterpret_cast<const int*>(cc.dev + npow_off) : nullptr;
   const double* d_basis = cc.dev + ((tab_doubles + 1) & ~(size_t)1);
-  double* d_vk8 = cc.dev + ((tab_doubles + 1) & ~(size_t)1) + (size_t)KK * Jp;   // [numU] v of the quantising kernel
-  double* d_wk8 = d_vk8 + numU;                                                   // [numU] basis row weights
-  unsigned char* d_b8 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(d_wk8 + numU) + 255) & ~(uintptr_t)255);
-  // Fixed-point tables of the int8 contraction for the transform g = kind / 2 (0 price, 1 delta,
-  // 2 gamma, 3 theta; OptionPricing.h:44-73): the transform multiplies phi by a factor of modulus (at
-  // most) f_k = 1, u_k, u_k sqrt(1 + u_k^2), 4 + |r|.  The quantising kernel stores (phi * factor) * v with v = sign(V_k) 2^45 / f_k
-  // -- a unit-modulus multiple of phi -- and the magnitude |V_k cp| f_k / amax moves to the basis
-  // planes.  Rebuilt when the strike grid or the transform changes.
-  const int q8g = kinds[0] >> 1;
-  if (use_i8 && (cc.q8_greek != q8g || (q8g == 3 && cc.q8_r != r))) {
-    std::vector<double> v8(numU), w8(numU);
-    double amax = 0.0;
-    for (int k = 0; k < numU; ++k) {
-      const double u = cc.uk_host[k];
-      // theta: -(log phi - r) phi, bounded by 1/e + pi + |r| for |phi| <= 1 (a constant "modulus")
-      const double f = q8g == 0 ? 1.0 : q8g == 1 ? u : q8g == 2 ? u * std::sqrt(1.0 + u * u) : 4.0 + std::fabs(r);
-      w8[k] = std::fabs(cc.vk_host[k]) * f;
-      v8[k] = (f > 0.0 && cc.vk_host[k] != 0.0) ? std::copysign(Q8_A_SCALE / f, cc.vk_host[k]) : 0.0;
-      amax = std::max(amax, w8[k]);
+  // Fixed-point tables of the int8 contraction (cos_gemm_i8.cuh).  Price, delta and gamma multiply phi
+  // by a factor c_k that does not depend on the parameters (1, i u_k, -(u_k^2 + i u_k);
+  // OptionPricing.h:44-73), so they share ONE set of coefficient planes (phi 2^45) and differ in the
+  // basis planes only: Bas_g[2k][j], Bas_g[2k+1][j] = Re, -Im of c_k e^{i u_k (x_j - x_0)} times
+  // V_k cp / amax_g.  Theta's factor -(log phi - r) depends on phi: it gets its own planes
+  // (transform / (4 + |r|), a bound on |phi (log phi - r)| for |phi| <= 1) over the price basis.
+  double* d_v8p = cc.dev + ((tab_doubles + 1) & ~(size_t)1) + (size_t)KK * Jp;   // [numU] 2^45
+  double* d_v8t = d_v8p + numU;                                                   // [numU] 2^45 / (4 + |r|)
+  const size_t b8_bytes = ((size_t)Q8_SLICES * J8 * KK + 255) & ~(size_t)255;
+  unsigned char* d_b8 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(d_v8t + numU) + 255) & ~(uintptr_t)255);
+  bool q8_price_planes = false, q8_theta_planes = false;
+  const double theta_bound = 4.0 + std::fabs(r);
+  if (use_i8) {
+    bool need_tab[3] = {false, false, false};
+    for (int i = 0; i < nk; ++i) {
+      const int g = kinds[i] >> 1;
+      if (g == 3) q8_theta_planes = true;
+      else q8_price_planes = true;
+      need_tab[g == 3 ? 0 : g] = true;
     }
-    cc.amax = amax;
-    if (amax > 0.0 && std::isfinite(amax)) {
-      for (int k = 0; k < numU; ++k) w8[k] /= amax;
-      FOP_CUDA(h, cudaStreamSynchronize(h->stream));  // earlier launches may still read the old tables
-      FOP_CUDA(h, cudaMemcpy(d_vk8, v8.data(), sizeof(double) * numU, cudaMemcpyHostToDevice));
-      FOP_CUDA(h, cudaMemcpy(d_wk8, w8.data(), sizeof(double) * numU, cudaMemcpyHostToDevice));
+    bool synced = false;
+    auto sync_once = [&]() -> int {  // earlier launches may still read the tables that are about to change
+      if (!synced) FOP_CUDA(h, cudaStreamSynchronize(h->stream));
+      synced = true;
+      return FOP_OK;
+    };
+    for (int g = 0; g < 3 && use_i8; ++g) {
+      if (!need_tab[g] || cc.q8_valid[g]) continue;
+      double amax = 0.0;
+      for (int k = 0; k < numU; ++k) {
+        const double u = cc.uk_host[k];
+        const double f = g == 0 ? 1.0 : g == 1 ? u : u * std::sqrt(1.0 + u * u);
+        amax = std::max(amax, std::fabs(cc.vk_host[k]) * f);
+      }
+      if (!(amax > 0.0) || !std::isfinite(amax)) {
+        use_i8 = false;
+        break;
+      }
+      FOP_TRY(sync_once());
       const long long n8 = (long long)J8 * KK;
       {
         ProfScope ps(h, "cos_basis_q8_kernel");
-        cos_basis_q8_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, h->stream>>>(d_basis, d_wk8, numU, KK, Jp, J, J8,
-                                                                                 d_b8);
+        cos_basis_q8_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, h->stream>>>(
+            cc.dev, cc.dev + numU, cc.dev + 2 * numU, g, 1.0 / amax, numU, KK, J, J8, d_b8 + (size_t)g * b8_bytes);
       }
       FOP_LAUNCH_CHECK(h);
-      cc.q8_greek = q8g;
-      cc.q8_r = r;
+      cc.q8_amax[g] = amax;
+      cc.q8_valid[g] = true;
+    }
+    if (use_i8 && q8_price_planes && !cc.q8_vp_valid) {
+      std::vector<double> v8(numU, Q8_A_SCALE);
+      FOP_TRY(sync_once());
+      FOP_CUDA(h, cudaMemcpy(d_v8p, v8.data(), sizeof(double) * numU, cudaMemcpyHostToDevice));
+      cc.q8_vp_valid = true;
+    }
+    if (use_i8 && q8_theta_planes && (!cc.q8_vt_valid || cc.q8_theta_bound != theta_bound)) {
+      std::vector<double> v8(numU, Q8_A_SCALE / theta_bound);
+      FOP_TRY(sync_once());
+      FOP_CUDA(h, cudaMemcpy(d_v8t, v8.data(), sizeof(double) * numU, cudaMemcpyHostToDevice));
+      cc.q8_vt_valid = true;
+      cc.q8_theta_bound = theta_bound;
     }
   }
-  if (use_i8 && (cc.q8_greek != q8g || !(cc.amax > 0.0))) use_i8 = false;
   if (use_i8) nblk = 2 * nblk8;  // two partial row losses per (set, maturity, strike block): one per column half
 
   const bool out_host = out && !is_device_ptr(out);
@@ -291,7 +316,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   need += fused ? Arena::pad((size_t)P * sizeof(ModelConsts)) : Arena::pad((size_t)chunk_rows * KK * 8 * ngreeks);
   if (out_host) need += Arena::pad((size_t)chunk_rows * J * 8);
   if (loss) need += Arena::pad((size_t)P * M * lossblk * 8) + (loss_host ? Arena::pad((size_t)P * 8) : 0);
-  if (use_i8) need += Arena::pad((size_t)chunk_rows);
+  if (use_i8) need += Arena::pad(2 * (size_t)chunk_rows);
   FOP_TRY(ar.reserve(need));
 
   const double *d_params = nullptr, *d_mkt = nullptr, *d_w = nullptr;
@@ -306,12 +331,14 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   double* d_out_tmp = out_host ? ar.alloc<double>((size_t)chunk_rows * J) : nullptr;
   double* d_rowloss = loss ? ar.alloc<double>((size_t)P * M * lossblk) : nullptr;
   double* d_loss = loss ? (loss_host ? ar.alloc<double>(P) : loss) : nullptr;
-  unsigned char* d_rowflag = use_i8 ? ar.alloc<unsigned char>((size_t)chunk_rows) : nullptr;
-  CUtensorMap tmB8;
+  unsigned char* d_rowflag = use_i8 ? ar.alloc<unsigned char>(2 * (size_t)chunk_rows) : nullptr;  // price | theta planes
+  CUtensorMap tmB8[3];
   if (use_i8) {
-    if (!make_tmap_3d_u8(&tmB8, d_b8, (unsigned long long)KK, (unsigned long long)J8, Q8_SLICES,
-                         (unsigned long long)KK, (unsigned long long)J8 * KK, Q8_KC, Q8_NQ, Q8_SLICES))
-      return fail(h, FOP_CUDA_ERROR, "tensor map (basis digit planes) could not be encoded");
+    for (int g = 0; g < 3; ++g)
+      if (cc.q8_valid[g] &&
+          !make_tmap_3d_u8(&tmB8[g], d_b8 + (size_t)g * b8_bytes, (unsigned long long)KK, (unsigned long long)J8, Q8_SLICES,
+                           (unsigned long long)KK, (unsigned long long)J8 * KK, Q8_KC, Q8_NQ, Q8_SLICES))
+        return fail(h, FOP_CUDA_ERROR, "tensor map (basis digit planes) could not be encoded");
     FOP_CUDA(h, cudaFuncSetAttribute(cos_gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)cos_i8_smem(M)));
   }
@@ -379,6 +406,58 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
         cos_coeff_samples_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(sa);
       }
       FOP_LAUNCH_CHECK(h);
+    } else if (use_i8) {
+      // digit planes in place of the fp64 matrix (6 of its 8 bytes per entry): one set for price / delta /
+      // gamma (phi itself), one for theta; then one contraction per requested kind
+      unsigned char* planes[2] = {reinterpret_cast<unsigned char*>(d_C), nullptr};
+      planes[1] = planes[0] + (q8_price_planes ? (size_t)chunk_rows * KK * Q8_SLICES : 0);
+      unsigned char* flags[2] = {d_rowflag, d_rowflag + chunk_rows};
+      FOP_CUDA(h, cudaMemsetAsync(d_rowflag, 0, 2 * (size_t)chunk_rows, h->stream));
+      for (int set = 0; set < 2; ++set) {
+        if (!(set == 0 ? q8_price_planes : q8_theta_planes)) continue;
+        CosCoeffArgs ca;
+        ca.base = model.base;  ca.tc = model.time_change;
+        ca.greek_mask = set == 0 ? 1 : 8;  ca.plane = 0;
+        ca.P = pc;  ca.M = M;  ca.K = numU;  ca.Kp = KK / 2;  ca.np = np;  ca.spb = 1;
+        ca.r = r;
+        ca.params = d_params + (size_t)p0 * np;
+        ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = set == 0 ? d_v8p : d_v8t;
+        ca.C = nullptr;  ca.C8 = planes[set];  ca.rowflag = flags[set];
+        {
+          ProfScope ps(h, "cos_coeff_kernel");
+          if (!cos_coeff_launch_spec(h, ca, 32)) return fail(h, FOP_INVALID_ARG, "no quantising coefficient kernel");
+        }
+        FOP_LAUNCH_CHECK(h);
+      }
+      for (int ik = 0; ik < nk; ++ik) {
+        const int kind = kinds[ik], g = kind >> 1, set = g == 3 ? 1 : 0, tb = g == 3 ? 0 : g;
+        double* out_k = out ? out + (size_t)ik * P * M * J + (size_t)p0 * M * J : nullptr;
+        CosGemmI8Args qa;
+        qa.kind = kind;  qa.M = M;  qa.J = J;  qa.KK = KK;  qa.nblk = nblk8;  qa.rows = rows;  qa.r = r;  qa.S0 = S0;
+        qa.amax = cc.q8_amax[tb] * (g == 3 ? theta_bound : 1.0);
+        qa.T = d_T;  qa.strikes = d_K;
+        qa.out = out ? (out_host ? d_out_tmp : out_k) : nullptr;
+        qa.vec2 = (J % 2 == 0) && (reinterpret_cast<uintptr_t>(qa.out) % 16 == 0);
+        qa.mkt = d_mkt;  qa.w = d_w;
+        qa.rowloss = (loss && ik == 0) ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
+        qa.rowflag = flags[set];
+        CUtensorMap tmA8;
+        // [rows][6 planes][KK] bytes, addressed as (kk, row, plane)
+        if (!make_tmap_3d_u8(&tmA8, planes[set], (unsigned long long)KK, (unsigned long long)rows, Q8_SLICES,
+                             (unsigned long long)Q8_SLICES * KK, (unsigned long long)KK, Q8_KC, Q8_ROWS, 1))
+          return fail(h, FOP_CUDA_ERROR, "tensor map (coefficient digit planes) could not be encoded");
+        const long long ntiles = (rows + Q8_ROWS - 1) / Q8_ROWS;
+        {
+          ProfScope ps(h, "cos_gemm_kernel");
+          // persistent, one CTA per SM: the SMs are divided among the strike blocks
+          const dim3 qgrid((unsigned)std::min<long long>(ntiles, std::max(1, h->sm_count / nblk8)), (unsigned)nblk8);
+          cos_gemm_i8_kernel<<<qgrid, Q8_THREADS, cos_i8_smem(M), h->stream>>>(qa, tmA8, tmB8[tb]);
+        }
+        FOP_LAUNCH_CHECK(h);
+        if (out_host)
+          FOP_CUDA(h, cudaMemcpyAsync(out_k, d_out_tmp, (size_t)rows * J * 8, cudaMemcpyDeviceToHost, h->stream));
+      }
+      continue;
     } else {
       CosCoeffArgs ca;
       ca.base = model.base;  ca.tc = model.time_change;
@@ -389,21 +468,12 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ca.params = d_params + (size_t)p0 * np;
       ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = d_C;
       ca.C8 = nullptr;  ca.rowflag = nullptr;
-      if (use_i8) {  // digit planes in place of the fp64 matrix (6 of its 8 bytes per entry)
-        ca.C8 = reinterpret_cast<unsigned char*>(d_C);
-        ca.rowflag = d_rowflag;
-        ca.plane = 0;
-        ca.vk = d_vk8;
-        FOP_CUDA(h, cudaMemsetAsync(d_rowflag, 0, (size_t)rows, h->stream));
-      }
       const int ngroups = (pc + ca.spb - 1) / ca.spb;
       const int cgrid = std::min(ngroups, h->sm_count * 32);
       {
         ProfScope ps(h, "cos_coeff_kernel");
         // default: model-specialised kernel (capi_cos_coeff.cu); FOP_COEFF_GENERIC=1: the generic one
-        if (use_i8) {
-          if (!cos_coeff_launch_spec(h, ca, 32)) return fail(h, FOP_INVALID_ARG, "no quantising coefficient kernel");
-        } else if (std::getenv("FOP_COEFF_GENERIC") || !cos_coeff_launch_spec(h, ca, 32)) {
+        if (std::getenv("FOP_COEFF_GENERIC") || !cos_coeff_launch_spec(h, ca, 32)) {
           int ilp = M >= 2 ? 2 : 1;
           if (const char* e = std::getenv("FOP_COEFF_ILP")) ilp = std::max(1, std::min(atoi(e), M >= 2 ? 2 : 1));
           if (ilp >= 2) cos_coeff_kernel<2><<<cgrid, 256, 0, h->stream>>>(ca);
@@ -411,34 +481,6 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
         }
       }
       FOP_LAUNCH_CHECK(h);
-    }
-    if (use_i8) {
-      double* out_k = out ? out + (size_t)p0 * M * J : nullptr;
-      CosGemmI8Args qa;
-      qa.kind = kinds[0];  qa.M = M;  qa.J = J;  qa.KK = KK;  qa.nblk = nblk8;  qa.rows = rows;  qa.r = r;  qa.S0 = S0;
-      qa.amax = cc.amax;  qa.T = d_T;  qa.strikes = d_K;
-      qa.out = out ? (out_host ? d_out_tmp : out_k) : nullptr;
-      qa.vec2 = (J % 2 == 0) && (reinterpret_cast<uintptr_t>(qa.out) % 16 == 0);
-      qa.mkt = d_mkt;  qa.w = d_w;
-      qa.rowloss = loss ? d_rowloss + (size_t)p0 * M * nblk : nullptr;
-      qa.rowflag = d_rowflag;
-      CUtensorMap tmA8;
-      // [rows][6 planes][KK] bytes, addressed as (kk, row, plane)
-      if (!make_tmap_3d_u8(&tmA8, reinterpret_cast<const unsigned char*>(d_C), (unsigned long long)KK,
-                           (unsigned long long)rows, Q8_SLICES, (unsigned long long)Q8_SLICES * KK,
-                           (unsigned long long)KK, Q8_KC, Q8_ROWS, 1))
-        return fail(h, FOP_CUDA_ERROR, "tensor map (coefficient digit planes) could not be encoded");
-      const long long ntiles = (rows + Q8_ROWS - 1) / Q8_ROWS;
-      {
-        ProfScope ps(h, "cos_gemm_kernel");
-        // persistent, one CTA per SM: the SMs are divided among the strike blocks
-        const dim3 qgrid((unsigned)std::min<long long>(ntiles, std::max(1, h->sm_count / nblk8)), (unsigned)nblk8);
-        cos_gemm_i8_kernel<<<qgrid, Q8_THREADS, cos_i8_smem(M), h->stream>>>(qa, tmA8, tmB8);
-      }
-      FOP_LAUNCH_CHECK(h);
-      if (out_host)
-        FOP_CUDA(h, cudaMemcpyAsync(out_k, d_out_tmp, (size_t)rows * J * 8, cudaMemcpyDeviceToHost, h->stream));
-      continue;
     }
     for (int ik = 0; ik < nk; ++ik) {
       const int kind = kinds[ik];

@@ -19,8 +19,9 @@ bool cos_coeff_launch_spec(fop_handle_t h, const CosCoeffArgs& a_in, int grid_bl
   if (a.C8) shape = shape == 1 ? ((a.Kp == 256 && a.base == BASE_GAUSS && a.tc == TC_CIR && a.npow) ? 102 : 101) : 100;
   if (a.C8 && a.greek_mask != 1) shape = 100;
   const bool grid = a.npow != nullptr;
-  // one compile-time transform: price (both outputs), or delta / gamma / theta with the quantised output
-  const int gsel = a.greek_mask == 1 ? 1 : (a.C8 && (a.greek_mask == 2 || a.greek_mask == 4 || a.greek_mask == 8)) ? a.greek_mask : -1;
+  // one compile-time transform: price (both outputs; its planes also serve delta and gamma), or theta
+  // with the quantised output
+  const int gsel = a.greek_mask == 1 ? 1 : (a.C8 && a.greek_mask == 8) ? 8 : -1;
   if (a.C8 && gsel < 0) return false;
   int nt = 256;
   CoeffKernel k = nullptr;

@@ -173,12 +173,12 @@ __host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, cons
     return;
   }
   if constexpr (std::is_same<CP, Q8Row>::value) {
-    // quantised output of ONE transform (GMASK = 2 delta, 4 gamma, 8 theta): v carries 2^45 / (bound of
-    // the transform factor), so the stored value is phi times a factor of modulus <= 1 (cos_gemm_i8.cuh;
-    // theta: |phi (log phi - r)| <= 1/e + pi + |r| for |phi| <= 1)
-    static_assert(GMASK == 1 || GMASK == 2 || GMASK == 4 || GMASK == 8, "quantised output: one transform");
+    // quantised theta planes (GMASK = 8; price, delta and gamma are contracted from the price planes
+    // above with their transform factor in the basis): v carries 2^45 / (4 + |r|), a bound of
+    // |phi (log phi - r)| <= 1/e + pi + |r| for |phi| <= 1 (cos_gemm_i8.cuh)
+    static_assert(GMASK == 1 || GMASK == 8, "quantised output: price or theta planes");
     const cx<VD<N>> d = cexp(lphi);
-    const cx<VD<N>> t = option_transform(GMASK == 2 ? 1 : GMASK == 4 ? 2 : 3, d, u, a.r);
+    const cx<VD<N>> t = option_transform(3, d, u, a.r);
 #pragma unroll
     for (int i = 0; i < N; ++i) coeff_store(a, crow, i, Kp, t.x.v[i] * v, t.y.v[i] * v);
   } else {

@@ -17,7 +17,7 @@ constexpr int kNumCoeffShapes = sizeof(kCoeffShapes) / sizeof(kCoeffShapes[0]);
 template <int BASE, int TC, bool GRID, int GMASK>
 CoeffKernel coeff_pick_shape(int shape, int* nt) {
   // shape >= 100: quantised output (digit planes for the int8 contraction; one transform)
-  if constexpr (GMASK == 2 || GMASK == 4 || GMASK == 8) {
+  if constexpr (GMASK == 8) {
     if (shape >= 100) {
       *nt = 256;
       return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 256, 2, true, true>;
@@ -43,13 +43,11 @@ CoeffKernel coeff_pick_shape(int shape, int* nt) {
   return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 256, 2>;
 }
 
-// gsel: -1 = run-time transform mask (fp64 output), 1 = price only, 2 / 4 / 8 = delta / gamma / theta only
-// (the latter three exist with the quantised output only)
+// gsel: -1 = run-time transform mask (fp64 output), 1 = price only, 8 = theta only (quantised output only;
+// delta and gamma are contracted from the price planes)
 template <int BASE, int TC, bool GRID>
 CoeffKernel coeff_pick_mask(int gsel, int shape, int* nt) {
   if (gsel == 1) return coeff_pick_shape<BASE, TC, GRID, 1>(shape, nt);
-  if (gsel == 2) return coeff_pick_shape<BASE, TC, GRID, 2>(shape, nt);
-  if (gsel == 4) return coeff_pick_shape<BASE, TC, GRID, 4>(shape, nt);
   if (gsel == 8) return coeff_pick_shape<BASE, TC, GRID, 8>(shape, nt);
   return coeff_pick_shape<BASE, TC, GRID, -1>(shape, nt);
 }

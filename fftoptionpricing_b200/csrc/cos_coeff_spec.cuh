@@ -33,7 +33,7 @@ __device__ __noinline__ void coeff_det_cold(const double* T, int M, double r, in
 template <int BASE, int TC, int ILP, bool GRID, int GMASK, int NT, int MINB, bool FAST = true, bool Q8 = false,
           int KPC = 0>
 __global__ void __launch_bounds__(NT, MINB) cos_coeff_kernel_s(const CosCoeffArgs a) {
-  static_assert(!Q8 || GMASK == 1 || GMASK == 2 || GMASK == 4 || GMASK == 8, "the quantised output carries ONE transform");
+  static_assert(!Q8 || GMASK == 1 || GMASK == 8, "the quantised output carries the price or the theta planes");
   using CP = typename std::conditional<Q8, Q8Row, double2*>::type;
   __shared__ ModelConsts consts[COEFF_MAX_SPB];
   const int tid = threadIdx.x;

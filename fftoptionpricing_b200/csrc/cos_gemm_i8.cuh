@@ -7,8 +7,8 @@
 //
 // so both operands are FIXED-POINT numbers with a scale known before the launch.  The magnitude of
 // V_k cp (it decays like 1/k) is moved to the basis so that every coefficient uses its full range:
-//   C'[row][kk] = sign(V_k) (Re | Im) phi       = qa 2^-45,   qa integer, |qa| <= 2^45   (coefficient kernel)
-//   Bas'[kk][j] = Bas[kk][j] |V_k cp| / amax    = qb 2^-46,   qb integer, |qb| <= 2^46   (once per strike grid)
+//   C'[row][kk] = (Re | Im) phi                 = qa 2^-45,   qa integer, |qa| <= 2^45   (coefficient kernel)
+//   Bas'[kk][j] = Bas[kk][j] V_k cp / amax      = qb 2^-46,   qb integer, |qb| <= 2^46   (once per strike grid)
 //   val = amax sum_kk C' Bas',   amax = max_k |V_k cp|
 // Each integer is split into six signed base-256 digits (int8): q = sum_s d_s 256^s.  The product of
 // two digit planes is an EXACT int8 x int8 -> int32 tensor-core GEMM (products <= 2^14, at most six
@@ -95,19 +95,33 @@ __host__ inline size_t cos_i8_smem(int M) {
 }
 
 // basis digit planes B8[6][J8][KK] (K-major: one row of KK bytes per strike; J8 = strike count padded
-// to whole 72-column blocks) from basis[KK][Jp], row kk weighted by |V_k cp| / amax (scaling note above)
-static __global__ void cos_basis_q8_kernel(const double* __restrict__ basis, const double* __restrict__ wk,
-                                           int numU, int KK, int Jp, int J, int J8,
-                                           unsigned char* __restrict__ B8) {
+// to whole 72-column blocks) of transform g (0 price, 1 delta, 2 gamma; OptionPricing.h:44-73): the
+// transform multiplies phi(i u_k) by c_k = 1, i u_k, -(u_k^2 + i u_k), a factor that does not depend on
+// the parameter set, so it lives HERE and the coefficient planes are phi itself:
+//   Re((a + i b) z) = a Re z - b Im z,  z = c_k e^{i u_k (x_j - x_0)}  ->  rows 2k, 2k + 1 = Re z, -Im z,
+// times V_k cp / amax_g (scaling note above).
+static __global__ void cos_basis_q8_kernel(const double* __restrict__ uk, const double* __restrict__ vk,
+                                           const double* __restrict__ x, int g, double inv_amax, int numU,
+                                           int KK, int J, int J8, unsigned char* __restrict__ B8) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= J8 * KK) return;
   const int j = idx / KK, kk = idx - j * KK;
-  const double v = (j < J && kk < 2 * numU) ? basis[(size_t)kk * Jp + j] * wk[kk >> 1] : 0.0;
+  const int k = kk >> 1;
+  double v = 0.0;
+  if (j < J && k < numU) {
+    const double u = uk[k];
+    double sn, cs;
+    sincos(u * (x[j] - x[0]), &sn, &cs);
+    const double fr = g == 0 ? 1.0 : g == 1 ? 0.0 : -u * u;
+    const double fi = g == 0 ? 0.0 : g == 1 ? u : -u;
+    const double zr = fr * cs - fi * sn, zi = fr * sn + fi * cs;
+    v = ((kk & 1) ? -zi : zr) * (vk[k] * inv_amax);
+  }
   unsigned lo, hi;
   q8_digits(v * Q8_B_SCALE, lo, hi);   // |v| <= 1: always representable
-  const unsigned long long u = lo | ((unsigned long long)hi << 32);
+  const unsigned long long u8 = lo | ((unsigned long long)hi << 32);
 #pragma unroll
-  for (int s = 0; s < Q8_SLICES; ++s) B8[((size_t)s * J8 + j) * KK + kk] = (unsigned char)(u >> (8 * s));
+  for (int s = 0; s < Q8_SLICES; ++s) B8[((size_t)s * J8 + j) * KK + kk] = (unsigned char)(u8 >> (8 * s));
 }
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {

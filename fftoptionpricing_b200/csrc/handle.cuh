@@ -33,9 +33,12 @@ struct fop_handle_s {
     int numU = 0, Jp = 0, JB = 0, KK = 0;
     double* dev = nullptr;  // [uk | vk | x | K | T | basis | vk8 | basis digit planes]
     size_t bytes = 0;
-    double amax = 0;        // max_k |vk| f_k: fixed-point scale of the int8 contraction (cos_gemm_i8.cuh)
-    int q8_greek = -1;      // transform (0 price, 1 delta, 2 gamma, 3 theta) the int8 tables are built for
-    double q8_r = 0;        // ... and the rate they assume (theta's bound 4 + |r|)
+    // fixed-point tables of the int8 contraction (cos_gemm_i8.cuh), built on demand: basis digit planes
+    // of price / delta / gamma with their scales amax_g, the coefficient kernel's scale tables
+    bool q8_valid[3] = {false, false, false};
+    double q8_amax[3] = {0, 0, 0};
+    bool q8_vp_valid = false, q8_vt_valid = false;
+    double q8_theta_bound = 0;   // 4 + |r| the theta scale table was built for
     std::vector<double> uk_host, vk_host;
   } cos_cache;
   // optional NCCL communicator (capi_comm.cu; opaque here, NCCL is bound at run time)

@@ -89,7 +89,7 @@ def test_i8_strike_counts(J, engine, best_oracle, monkeypatch):
 @pytest.mark.parametrize("M,expect", [(1, "int8-tcgen05"), (16, "int8-tcgen05"), (17, "fp64-dmma"), (40, "fp64-dmma")])
 def test_i8_maturity_count_boundary(M, expect, engine, best_oracle):
     """Up to 16 maturities the market tables of a strike block fit next to the operand rings; longer
-    lists fall back to the fp64 kernels, and so do calls asking for several kinds at once."""
+    lists fall back to the fp64 kernels (single- and multi-kind calls alike)."""
     prm = CASES.heston_batch(3)
     K = 100.0 * np.linspace(1.5, 0.5, 30)
     T = list(np.linspace(0.1, 2.0, M))
@@ -97,8 +97,8 @@ def test_i8_maturity_count_boundary(M, expect, engine, best_oracle):
     assert engine.last_cos_contraction == expect
     ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 128, 1)
     assert_parity(got, ref, what=f"M={M}")
-    engine.cos_greeks(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T[:2], 128, [0, 6])   # two kinds, one CF pass
-    assert engine.last_cos_contraction == "fp64-dmma"
+    monkey_kinds = engine.cos_greeks(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.01, T, 128, [0, 6])
+    assert engine.last_cos_contraction == expect and monkey_kinds.shape == (2, 3, M, 30)
 
 
 def test_i8_loss_over_strike_blocks(engine, monkeypatch):
@@ -204,9 +204,9 @@ def test_i8_u_count_limit_falls_back(engine, best_oracle):
 @pytest.mark.parametrize("kind", [2, 3, 4, 5, 6, 7])
 def test_i8_greeks(kind, engine, best_oracle, monkeypatch):
     """Call / put delta, gamma and theta (one kind per call) through the int8 kernel: the transform
-    factor (i u, -i u (1 - i u), resp. -(log phi - r), OptionPricing.h:44-73) has its modulus -- for theta
-    its bound 4 + |r| -- moved to the basis planes, so the coefficient is still phi times a factor of
-    modulus at most one."""
+    factor of delta and gamma (i u, -i u (1 - i u); OptionPricing.h:44-73) does not depend on the
+    parameter set and lives in the basis planes -- they are contracted from the price planes --, theta's
+    -(log phi - r) gets its own planes scaled by its bound 4 + |r|."""
     prm = CASES.heston_batch(33)
     K = CASES.c5_strikes()
     T = [0.25, 1.0, 2.0]
@@ -220,7 +220,7 @@ def test_i8_greeks(kind, engine, best_oracle, monkeypatch):
 
 def test_i8_tables_follow_the_requested_kind(engine, best_oracle):
     """price -> delta -> gamma -> theta -> price on one handle (and theta at another rate): the cached
-    fixed-point tables are rebuilt per transform; multi-kind calls take the fp64 kernels."""
+    fixed-point tables are built per transform on demand."""
     prm = CASES.heston_batch(6)
     K = 100.0 * np.linspace(1.5, 0.5, 24)
     T = [0.5, 1.5]
@@ -229,8 +229,14 @@ def test_i8_tables_follow_the_requested_kind(engine, best_oracle):
         assert engine.last_cos_contraction == "int8-tcgen05"
         ref = best_oracle.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, r, T, 256, kind)
         assert_parity(got, ref, what=f"kind {kind} after a table switch")
-    engine.cos_greeks(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, T, 256, [0, 2, 4, 6])
-    assert engine.last_cos_contraction == "fp64-dmma"
+    # several kinds in one call: price, delta and gamma share ONE set of coefficient planes (phi itself;
+    # their transform factors live in the basis planes), theta has its own -- same bits as kind by kind
+    kinds = [0, 2, 4, 6, 1, 5]
+    many = engine.cos_greeks(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, T, 256, kinds)
+    assert engine.last_cos_contraction == "int8-tcgen05"
+    for i, kind in enumerate(kinds):
+        one = engine.cos(CASES.GAUSS, CASES.TC_CIR, prm, K, 100.0, 0.02, T, 256, kind)
+        assert np.array_equal(many[i], one), f"kind {kind}"
 
 
 @pytest.mark.parametrize("model", ["merton", "cgmy", "cgmy_cir_diffusion"])
