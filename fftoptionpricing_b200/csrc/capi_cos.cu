@@ -379,7 +379,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ca.r = r;
       ca.params = d_params + (size_t)p0 * np;
       ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = nullptr;
-      ca.C8 = nullptr;  ca.rowflag = nullptr;
+      ca.C8 = nullptr;  ca.rowflag = nullptr;  ca.q8_theta_scale = 0.0;
       fa.kind = kind;  fa.J = J;  fa.nchunks = KK / FW_KC;  fa.SPT = spt;  fa.depth = 0;
       fa.S0 = S0;
       fa.consts = d_consts + p0;
@@ -413,11 +413,14 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       planes[1] = planes[0] + (q8_price_planes ? (size_t)chunk_rows * KK * Q8_SLICES : 0);
       unsigned char* flags[2] = {d_rowflag, d_rowflag + chunk_rows};
       FOP_CUDA(h, cudaMemsetAsync(d_rowflag, 0, 2 * (size_t)chunk_rows, h->stream));
+      const bool both = q8_price_planes && q8_theta_planes;   // one evaluation feeds both sets of planes
       for (int set = 0; set < 2; ++set) {
-        if (!(set == 0 ? q8_price_planes : q8_theta_planes)) continue;
+        if (!(set == 0 ? q8_price_planes : q8_theta_planes) || (both && set == 1)) continue;
         CosCoeffArgs ca;
         ca.base = model.base;  ca.tc = model.time_change;
-        ca.greek_mask = set == 0 ? 1 : 8;  ca.plane = 0;
+        ca.greek_mask = both ? 9 : set == 0 ? 1 : 8;
+        ca.plane = both ? (size_t)chunk_rows * KK * Q8_SLICES : 0;   // bytes from the price to the theta planes
+        ca.q8_theta_scale = Q8_A_SCALE / theta_bound;
         ca.P = pc;  ca.M = M;  ca.K = numU;  ca.Kp = KK / 2;  ca.np = np;  ca.spb = 1;
         ca.r = r;
         ca.params = d_params + (size_t)p0 * np;
@@ -467,7 +470,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ca.r = r;
       ca.params = d_params + (size_t)p0 * np;
       ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = d_C;
-      ca.C8 = nullptr;  ca.rowflag = nullptr;
+      ca.C8 = nullptr;  ca.rowflag = nullptr;  ca.q8_theta_scale = 0.0;
       const int ngroups = (pc + ca.spb - 1) / ca.spb;
       const int cgrid = std::min(ngroups, h->sm_count * 32);
       {

@@ -21,7 +21,7 @@ bool cos_coeff_launch_spec(fop_handle_t h, const CosCoeffArgs& a_in, int grid_bl
   const bool grid = a.npow != nullptr;
   // one compile-time transform: price (both outputs; its planes also serve delta and gamma), or theta
   // with the quantised output
-  const int gsel = a.greek_mask == 1 ? 1 : (a.C8 && a.greek_mask == 8) ? 8 : -1;
+  const int gsel = a.greek_mask == 1 ? 1 : (a.C8 && (a.greek_mask == 8 || a.greek_mask == 9)) ? a.greek_mask : -1;
   if (a.C8 && gsel < 0) return false;
   int nt = 256;
   CoeffKernel k = nullptr;

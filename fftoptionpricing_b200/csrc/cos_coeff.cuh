@@ -33,6 +33,7 @@ struct CosCoeffArgs {
   // (NaN / overflow): the contraction turns such rows into NaN like the fp64 path would.
   unsigned char* C8;
   unsigned char* rowflag;
+  double q8_theta_scale;   // greek_mask 9 (price AND theta planes from one evaluation): 2^45 / (4 + |r|)
 };
 
 // ---- fixed-point digit planes (int8 contraction) ---------------------------------------------
@@ -176,11 +177,21 @@ __host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, cons
     // quantised theta planes (GMASK = 8; price, delta and gamma are contracted from the price planes
     // above with their transform factor in the basis): v carries 2^45 / (4 + |r|), a bound of
     // |phi (log phi - r)| <= 1/e + pi + |r| for |phi| <= 1 (cos_gemm_i8.cuh)
-    static_assert(GMASK == 1 || GMASK == 8, "quantised output: price or theta planes");
+    // GMASK = 9: both sets from one evaluation -- the theta planes lie a.plane bytes behind the price
+    // planes (and their row flags chunk-rows behind, which the row index of coeff_store yields by itself)
+    static_assert(GMASK == 1 || GMASK == 8 || GMASK == 9, "quantised output: price and / or theta planes");
     const cx<VD<N>> d = cexp(lphi);
+    CP ct = crow;
+    double vt = v;
+    if (GMASK == 9) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) coeff_store(a, crow, i, Kp, d.x.v[i] * v, d.y.v[i] * v);
+      ct.p += a.plane / 2;
+      vt = a.q8_theta_scale;
+    }
     const cx<VD<N>> t = option_transform(3, d, u, a.r);
 #pragma unroll
-    for (int i = 0; i < N; ++i) coeff_store(a, crow, i, Kp, t.x.v[i] * v, t.y.v[i] * v);
+    for (int i = 0; i < N; ++i) coeff_store(a, ct, i, Kp, t.x.v[i] * vt, t.y.v[i] * vt);
   } else {
     const cx<VD<N>> d = cexp(lphi);
     // one CF evaluation feeds every requested transform (price / delta / gamma / theta)

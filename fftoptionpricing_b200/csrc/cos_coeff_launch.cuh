@@ -17,7 +17,7 @@ constexpr int kNumCoeffShapes = sizeof(kCoeffShapes) / sizeof(kCoeffShapes[0]);
 template <int BASE, int TC, bool GRID, int GMASK>
 CoeffKernel coeff_pick_shape(int shape, int* nt) {
   // shape >= 100: quantised output (digit planes for the int8 contraction; one transform)
-  if constexpr (GMASK == 8) {
+  if constexpr (GMASK == 8 || GMASK == 9) {
     if (shape >= 100) {
       *nt = 256;
       return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 256, 2, true, true>;
@@ -43,12 +43,13 @@ CoeffKernel coeff_pick_shape(int shape, int* nt) {
   return cos_coeff_kernel_s<BASE, TC, 2, GRID, GMASK, 256, 2>;
 }
 
-// gsel: -1 = run-time transform mask (fp64 output), 1 = price only, 8 = theta only (quantised output only;
+// gsel: -1 = run-time transform mask (fp64 output), 1 = price only, 8 = theta only, 9 = price and theta planes (quantised output only;
 // delta and gamma are contracted from the price planes)
 template <int BASE, int TC, bool GRID>
 CoeffKernel coeff_pick_mask(int gsel, int shape, int* nt) {
   if (gsel == 1) return coeff_pick_shape<BASE, TC, GRID, 1>(shape, nt);
   if (gsel == 8) return coeff_pick_shape<BASE, TC, GRID, 8>(shape, nt);
+  if (gsel == 9) return coeff_pick_shape<BASE, TC, GRID, 9>(shape, nt);
   return coeff_pick_shape<BASE, TC, GRID, -1>(shape, nt);
 }
 

@@ -15,12 +15,12 @@ namespace fop {
 // cold path: rebuilt from scalars so that the kernel parameter block is not copied to the stack
 template <int BASE, int TC, int GMASK, class CP>
 __device__ __noinline__ void coeff_det_cold(const double* T, int M, double r, int greek_mask, size_t plane,
-                                            unsigned char* C8, unsigned char* rowflag,
+                                            unsigned char* C8, unsigned char* rowflag, double q8_theta_scale,
                                             const ModelConsts* mcp, double uy, double v, CP crow,
                                             int Kp) {
   CosCoeffArgs a;
   a.T = T;  a.M = M;  a.r = r;  a.greek_mask = greek_mask;  a.plane = plane;  a.npow = nullptr;  a.dt = 0.0;
-  a.C8 = C8;  a.rowflag = rowflag;  a.Kp = Kp;
+  a.C8 = C8;  a.rowflag = rowflag;  a.Kp = Kp;  a.q8_theta_scale = q8_theta_scale;
   const ModelConsts mc = *mcp;
   const cd u = mk(0.0, uy);
   CfPre pre;
@@ -33,7 +33,7 @@ __device__ __noinline__ void coeff_det_cold(const double* T, int M, double r, in
 template <int BASE, int TC, int ILP, bool GRID, int GMASK, int NT, int MINB, bool FAST = true, bool Q8 = false,
           int KPC = 0>
 __global__ void __launch_bounds__(NT, MINB) cos_coeff_kernel_s(const CosCoeffArgs a) {
-  static_assert(!Q8 || GMASK == 1 || GMASK == 8, "the quantised output carries the price or the theta planes");
+  static_assert(!Q8 || GMASK == 1 || GMASK == 8 || GMASK == 9, "the quantised output carries the price and / or the theta planes");
   using CP = typename std::conditional<Q8, Q8Row, double2*>::type;
   __shared__ ModelConsts consts[COEFF_MAX_SPB];
   const int tid = threadIdx.x;
@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(NT, MINB) cos_coeff_kernel_s(const CosCoeffArg
         crow.p = reinterpret_cast<unsigned short*>(a.C8) + (size_t)(p0 + s) * M * Q8_SLICES * Kp + k;
         if (k >= K) {
           for (int m = 0; m < M * Q8_SLICES; ++m) crow.p[(size_t)m * Kp] = 0;
+          if (GMASK == 9)
+            for (int m = 0; m < M * Q8_SLICES; ++m) crow.p[a.plane / 2 + (size_t)m * Kp] = 0;
           continue;
         }
       } else {
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(NT, MINB) cos_coeff_kernel_s(const CosCoeffArg
         cf_prepare(BASE, TC, mc, u, a.r, pre);
         coeff_maturities_g<CF_MODE_LEVY, ILP, false, GMASK, false, CP>(a, mc, pre, u, v, crow, Kp);
       } else if (mc.adaV == 0.0) {
-        coeff_det_cold<BASE, TC, GMASK, CP>(a.T, M, a.r, a.greek_mask, a.plane, a.C8, a.rowflag, &consts[s], u.y, v,
+        coeff_det_cold<BASE, TC, GMASK, CP>(a.T, M, a.r, a.greek_mask, a.plane, a.C8, a.rowflag, a.q8_theta_scale, &consts[s], u.y, v,
                                             crow, Kp);
       } else {
         CfPre pre;

@@ -107,8 +107,7 @@ int fop_synchronize(fop_handle_t handle);
 long long fop_launch_count(fop_handle_t handle);
 /* contraction kernel the last fop_cos* call on this handle used (for benchmarks / tests):
  * 0 none yet, 1 fp64 tensor cores (mma.sync DMMA), 2 int8 digit planes on tcgen05 / TMEM
- * (any ONE output kind per call, <= 16 maturities, numU <= 8192; FOP_GEMM_I8=0 disables it),
- * 3 fused single kernel */
+ * (model CFs, <= 16 maturities, numU <= 8192; FOP_GEMM_I8=0 disables it), 3 fused single kernel */
 int fop_last_cos_contraction(fop_handle_t handle);
 
 /* Optional per-kernel device timing: while enabled every kernel launch of this library is
