@@ -167,8 +167,12 @@ def test_all_greeks_from_one_cf_pass(engine, best_oracle):
         for i, kind in enumerate(kinds):
             ref = best_oracle.cos(base, tc, prm, K, 100.0, .03, T, 128, kind)
             assert_parity(got[i], ref, what=f"greeks kind={kind} model=({base},{tc})")
+        # a subset of the kinds gives the same values (to the last digit plane of the int8 contraction: with
+        # theta in the list the price planes come from the kernel that also writes the theta planes, whose
+        # FMA contraction may differ by an ulp of a coefficient)
         sub = engine.cos_greeks(base, tc, prm, K, 100.0, .03, T, 128, [5, 2])
-        assert np.array_equal(sub[0], got[5]) and np.array_equal(sub[1], got[2])
+        for a, b in ((sub[0], got[5]), (sub[1], got[2])):
+            assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max())
 
 
 def test_quotes_to_objective_end_to_end(engine):
