@@ -236,7 +236,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
   // V_k cp / amax_g.  Theta's factor -(log phi - r) depends on phi: it gets its own planes
   // (transform / (4 + |r|), a bound on |phi (log phi - r)| for |phi| <= 1) over the price basis.
   double* d_v8p = cc.dev + ((tab_doubles + 1) & ~(size_t)1) + (size_t)KK * Jp;   // [numU] 2^45
-  double* d_v8t = d_v8p + numU;                                                   // [numU] 2^45 / (4 + |r|)
+  double* d_v8t = d_v8p + numU;   // [numU] 2^45 / (4 + |r|); MUST follow d_v8p: the two-set kernel reads vk[numU]
   const size_t b8_bytes = ((size_t)Q8_SLICES * J8 * KK + 255) & ~(size_t)255;
   unsigned char* d_b8 = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(d_v8t + numU) + 255) & ~(uintptr_t)255);
   bool q8_price_planes = false, q8_theta_planes = false;
@@ -379,7 +379,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ca.r = r;
       ca.params = d_params + (size_t)p0 * np;
       ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = nullptr;
-      ca.C8 = nullptr;  ca.rowflag = nullptr;  ca.q8_theta_scale = 0.0;
+      ca.C8 = nullptr;  ca.rowflag = nullptr;
       fa.kind = kind;  fa.J = J;  fa.nchunks = KK / FW_KC;  fa.SPT = spt;  fa.depth = 0;
       fa.S0 = S0;
       fa.consts = d_consts + p0;
@@ -420,7 +420,6 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
         ca.base = model.base;  ca.tc = model.time_change;
         ca.greek_mask = both ? 9 : set == 0 ? 1 : 8;
         ca.plane = both ? (size_t)chunk_rows * KK * Q8_SLICES : 0;   // bytes from the price to the theta planes
-        ca.q8_theta_scale = Q8_A_SCALE / theta_bound;
         ca.P = pc;  ca.M = M;  ca.K = numU;  ca.Kp = KK / 2;  ca.np = np;  ca.spb = 1;
         ca.r = r;
         ca.params = d_params + (size_t)p0 * np;
@@ -470,7 +469,7 @@ int cos_run(fop_handle_t h, fop_model_t model, const double* params, int P, cons
       ca.r = r;
       ca.params = d_params + (size_t)p0 * np;
       ca.T = d_T;  ca.npow = d_npow;  ca.dt = cc.dt;  ca.uk = d_tab;  ca.vk = d_tab + numU;  ca.C = d_C;
-      ca.C8 = nullptr;  ca.rowflag = nullptr;  ca.q8_theta_scale = 0.0;
+      ca.C8 = nullptr;  ca.rowflag = nullptr;
       const int ngroups = (pc + ca.spb - 1) / ca.spb;
       const int cgrid = std::min(ngroups, h->sm_count * 32);
       {

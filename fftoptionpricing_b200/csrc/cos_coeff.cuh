@@ -33,7 +33,8 @@ struct CosCoeffArgs {
   // (NaN / overflow): the contraction turns such rows into NaN like the fp64 path would.
   unsigned char* C8;
   unsigned char* rowflag;
-  double q8_theta_scale;   // greek_mask 9 (price AND theta planes from one evaluation): 2^45 / (4 + |r|)
+  // (no further fields: with eight more bytes in this parameter block ptxas allocated the hot kernel 96
+  // instead of 92 registers and it ran 1 % slower -- the two-set kernel's theta scale travels in vk[K])
 };
 
 // ---- fixed-point digit planes (int8 contraction) ---------------------------------------------
@@ -173,7 +174,9 @@ __host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, cons
     for (int i = 0; i < N; ++i) coeff_store(a, crow, i, Kp, t.x.v[i], t.y.v[i]);
     return;
   }
-  if constexpr (std::is_same<CP, Q8Row>::value) {
+  if constexpr (GMASK == 1) {
+    // (price-only instantiation: nothing below is generated)
+  } else if constexpr (std::is_same<CP, Q8Row>::value) {
     // quantised theta planes (GMASK = 8; price, delta and gamma are contracted from the price planes
     // above with their transform factor in the basis): v carries 2^45 / (4 + |r|), a bound of
     // |phi (log phi - r)| <= 1/e + pi + |r| for |phi| <= 1 (cos_gemm_i8.cuh)
@@ -187,7 +190,7 @@ __host__ __device__ __forceinline__ void coeff_group(const CosCoeffArgs& a, cons
 #pragma unroll
       for (int i = 0; i < N; ++i) coeff_store(a, crow, i, Kp, d.x.v[i] * v, d.y.v[i] * v);
       ct.p += a.plane / 2;
-      vt = a.q8_theta_scale;
+      vt = a.vk[a.K];   // the theta scale table [numU] follows the price scale table (capi_cos.cu)
     }
     const cx<VD<N>> t = option_transform(3, d, u, a.r);
 #pragma unroll

@@ -15,12 +15,15 @@ namespace fop {
 // cold path: rebuilt from scalars so that the kernel parameter block is not copied to the stack
 template <int BASE, int TC, int GMASK, class CP>
 __device__ __noinline__ void coeff_det_cold(const double* T, int M, double r, int greek_mask, size_t plane,
-                                            unsigned char* C8, unsigned char* rowflag, double q8_theta_scale,
+                                            unsigned char* C8, unsigned char* rowflag,
                                             const ModelConsts* mcp, double uy, double v, CP crow,
                                             int Kp) {
   CosCoeffArgs a;
   a.T = T;  a.M = M;  a.r = r;  a.greek_mask = greek_mask;  a.plane = plane;  a.npow = nullptr;  a.dt = 0.0;
-  a.C8 = C8;  a.rowflag = rowflag;  a.Kp = Kp;  a.q8_theta_scale = q8_theta_scale;
+  a.C8 = C8;  a.rowflag = rowflag;  a.Kp = Kp;
+  // (the two-set kernel, GMASK = 9, reads its theta scale from vk[K]: 2^45 / (4 + |r|) as the host sets it)
+  const double theta_scale = 35184372088832.0 / (4.0 + fabs(r));
+  a.vk = &theta_scale;  a.K = 0;
   const ModelConsts mc = *mcp;
   const cd u = mk(0.0, uy);
   CfPre pre;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(NT, MINB) cos_coeff_kernel_s(const CosCoeffArg
         cf_prepare(BASE, TC, mc, u, a.r, pre);
         coeff_maturities_g<CF_MODE_LEVY, ILP, false, GMASK, false, CP>(a, mc, pre, u, v, crow, Kp);
       } else if (mc.adaV == 0.0) {
-        coeff_det_cold<BASE, TC, GMASK, CP>(a.T, M, a.r, a.greek_mask, a.plane, a.C8, a.rowflag, a.q8_theta_scale, &consts[s], u.y, v,
+        coeff_det_cold<BASE, TC, GMASK, CP>(a.T, M, a.r, a.greek_mask, a.plane, a.C8, a.rowflag, &consts[s], u.y, v,
                                             crow, Kp);
       } else {
         CfPre pre;

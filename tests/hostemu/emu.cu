@@ -54,7 +54,7 @@ extern "C" int emu_cos(int base, int tc, const double* params, int P, const doub
       a.params = params + (size_t)p * np;  a.T = Th.data();
       a.npow = dt > 0.0 ? steps.data() : nullptr;  a.dt = dt;
       a.uk = uk.data();  a.vk = vk.data();  a.C = reinterpret_cast<double*>(C.data());
-      a.C8 = nullptr;  a.rowflag = nullptr;  a.q8_theta_scale = 0.0;
+      a.C8 = nullptr;  a.rowflag = nullptr;
       ModelConsts mc;
       make_consts(base, tc, a.params, mc);
       const int mode = cf_mode(tc, mc);
