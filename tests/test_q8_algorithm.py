@@ -32,19 +32,19 @@ def digits(q):
     return np.stack(out)            # [6][...]
 
 
-def contract_q8(emu, phi, vk, basis):
-    """phi [rows][K] complex, vk [K], basis [2K][J] -> (val [rows][J], level sums [7][rows][J])."""
+def contract_q8(emu, phi, vk, basis, amax=None):
+    """phi [rows][K] complex, vk [K] (row weights of the basis), basis [2K][J] -> (val [rows][J], level
+    sums [7][rows][J])."""
     rows, K = phi.shape
-    amax = np.abs(vk).max()
-    sgn = np.sign(vk)
-    # coefficient kernel: C' = sign(V_k) (Re | Im) phi 2^45, quantised by the device code
-    qr, qi, flag, _ = emu.q8_store((phi.real * sgn * A_SCALE).ravel(), (phi.imag * sgn * A_SCALE).ravel())
+    amax = np.abs(vk).max() if amax is None else amax
+    # coefficient kernel: C' = (Re | Im) phi 2^45, quantised by the device code
+    qr, qi, flag, _ = emu.q8_store((phi.real * A_SCALE).ravel(), (phi.imag * A_SCALE).ravel())
     assert not flag.any()
     qa = np.empty((rows, 2 * K), dtype=np.int64)
     qa[:, 0::2] = qr.reshape(rows, K)
     qa[:, 1::2] = qi.reshape(rows, K)
-    # basis planes: Bas' = Bas |V_k| / amax 2^46 (cos_basis_q8_kernel)
-    qb = np.rint(basis * (np.repeat(np.abs(vk), 2) / amax)[:, None] * B_SCALE).astype(np.int64)
+    # basis planes: Bas' = Bas V_k / amax 2^46 (cos_basis_q8_kernel)
+    qb = np.rint(basis * (np.repeat(vk, 2) / amax)[:, None] * B_SCALE).astype(np.int64)
     a, b = digits(qa), digits(qb)                      # [6][rows][2K], [6][2K][J]
     S = np.zeros((LEVELS, rows, basis.shape[1]), dtype=np.int64)
     for s in range(SLICES):
@@ -89,3 +89,29 @@ def test_level_sums_use_the_int32_range_safely(emu):
     """Worst-case digits (+-128 everywhere) at the host's limit of 16 384 terms stay inside int32."""
     worst = 6 * 128 * 128 * 16384
     assert worst < 2**31
+
+
+@pytest.mark.parametrize("g", [1, 2])
+def test_delta_and_gamma_live_in_the_basis_planes(emu, g):
+    """The transform factor of delta (i u) and gamma (-(u^2 + i u)), OptionPricing.h:44-73, does not
+    depend on phi: Re(phi c_k V_k e^{i u_k x_j}) = Re(phi) Re(z) - Im(phi) Im(z) with z = c_k e^{i u_k x_j},
+    so the price planes (phi itself) contract against basis rows (Re z, -Im z) V_k / amax_g."""
+    K, J, rows = 256, 40, 9
+    rng = np.random.default_rng(g)
+    u = np.pi / 6.0 * np.arange(K)
+    x = np.linspace(0.0, 6.0, J)
+    vk = (2.0 / 6.0) * np.cos(u * 0.4) / (1.0 + u * u) - 0.1 / (1.0 + np.arange(K))
+    vk[0] *= 0.5
+    phi = np.exp(-0.03 * np.outer(rng.uniform(0.2, 3.0, rows), u * u)) * np.exp(1j * rng.uniform(-np.pi, np.pi, (rows, K)))
+    c = 1j * u if g == 1 else -(u * u + 1j * u)
+    z = c[:, None] * np.exp(1j * np.outer(u, x))                       # [K][J]
+    ref = np.einsum("rk,kj->rj", phi * vk, z).real                      # sum_k Re(phi c_k V_k e^{i u_k x_j})
+    basis = np.empty((2 * K, J))
+    basis[0::2] = z.real
+    basis[1::2] = -z.imag
+    f = np.abs(c)
+    amax = (np.abs(vk) * f).max()
+    fn = np.where(f > 0, f, 1.0)
+    basis_unit = basis / np.repeat(fn, 2)[:, None]                      # rows of modulus <= 1 ...
+    val, S = contract_q8(emu, phi, vk * f, basis_unit, amax=amax)       # ... times |c_k| V_k / amax_g
+    assert np.abs(val - ref).max() <= 64 * 2.0**-46 * amax * np.sqrt(2 * K)
